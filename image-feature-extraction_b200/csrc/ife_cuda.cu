@@ -1,0 +1,698 @@
+// libife_cuda.so -- host side of the C ABI declared in include/ife_cuda.h: context,
+// device workspace, coefficient set-up and kernel orchestration.  No CPU fallback: every
+// entry point fails with IFE_E_CUDA when no device is usable.
+#include "ife_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "eigen_features.cuh"
+#include "recursive_gaussian.cuh"
+#include "ife_ctx.h"
+
+namespace ife {
+
+int fail(ife_cuda_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->error = buf;
+  return code;
+}
+
+#define IFE_CUDA_TRY(ctx, expr)                                                              \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return ife::fail(ctx, e_ == cudaErrorMemoryAllocation ? IFE_E_NOMEM : IFE_E_CUDA,      \
+                       "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__,     \
+                       __LINE__);                                                            \
+  } while (0)
+
+#define IFE_TRY(expr)          \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != IFE_OK) return rc_; \
+  } while (0)
+
+int DeviceBuffer::reserve(ife_cuda_ctx* ctx, size_t want) {
+  if (want <= bytes) return IFE_OK;
+  if (ptr) {
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+  }
+  IFE_CUDA_TRY(ctx, cudaMalloc(&ptr, want));
+  bytes = want;
+  return IFE_OK;
+}
+
+void DeviceBuffer::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Coefficients of ITK's zero-order recursive Gaussian (Deriche 4th order with the
+// Farneback-Westin parameter set), unit DC gain, symmetric anticausal part, constant-
+// extension boundary terms.  sigma is physical; the recursion runs on samples.
+// Replaces RecursiveGaussianImageFilter::SetUp as reached from
+// include/ife/Filters/NormalizedGaussianConvolutionImageFilter.hxx:51-55.
+// ---------------------------------------------------------------------------------------
+GaussCoef make_gauss_coef(double sigma, double spacing) {
+  const double sd = spacing < 1e-8 ? sigma : sigma / spacing;
+  const double a[2] = {1.3530, -0.3531}, b[2] = {1.8151, 0.0902};
+  const double w[2] = {0.6681, 2.0787}, l[2] = {-1.3932, -1.3732};
+  double sn[2], cs[2], ex[2];
+  for (int i = 0; i < 2; ++i) {
+    sn[i] = std::sin(w[i] / sd);
+    cs[i] = std::cos(w[i] / sd);
+    ex[i] = std::exp(l[i] / sd);
+  }
+  GaussCoef c;
+  double* D = c.D;  // D[0] = D1 ...
+  D[3] = ex[0] * ex[0] * ex[1] * ex[1];
+  D[2] = -2 * cs[0] * ex[0] * ex[1] * ex[1];
+  D[2] += -2 * cs[1] * ex[1] * ex[0] * ex[0];
+  D[1] = 4 * cs[1] * cs[0] * ex[0] * ex[1];
+  D[1] += ex[0] * ex[0] + ex[1] * ex[1];
+  D[0] = -2 * (ex[1] * cs[1] + ex[0] * cs[0]);
+  const double SD = 1.0 + D[0] + D[1] + D[2] + D[3];
+
+  double* N = c.N;
+  N[0] = a[0] + a[1];
+  N[1] = ex[1] * (b[1] * sn[1] - (a[1] + 2 * a[0]) * cs[1]);
+  N[1] += ex[0] * (b[0] * sn[0] - (a[0] + 2 * a[1]) * cs[0]);
+  N[2] = (a[0] + a[1]) * cs[1] * cs[0];
+  N[2] -= b[0] * cs[1] * sn[0] + b[1] * cs[0] * sn[1];
+  N[2] *= 2 * ex[0] * ex[1];
+  N[2] += a[1] * ex[0] * ex[0] + a[0] * ex[1] * ex[1];
+  N[3] = ex[1] * ex[0] * ex[0] * (b[1] * sn[1] - a[1] * cs[1]);
+  N[3] += ex[0] * ex[1] * ex[1] * (b[0] * sn[0] - a[0] * cs[0]);
+  const double SN0 = N[0] + N[1] + N[2] + N[3];
+  const double alpha0 = 2 * SN0 / SD - N[0];
+  for (int i = 0; i < 4; ++i) N[i] *= 1.0 / alpha0;
+
+  c.M[0] = N[1] - D[0] * N[0];
+  c.M[1] = N[2] - D[1] * N[0];
+  c.M[2] = N[3] - D[2] * N[0];
+  c.M[3] = -D[3] * N[0];
+  const double SN = N[0] + N[1] + N[2] + N[3];
+  const double SM = c.M[0] + c.M[1] + c.M[2] + c.M[3];
+  for (int i = 0; i < 4; ++i) {
+    c.BN[i] = D[i] * SN / SD;
+    c.BM[i] = D[i] * SM / SD;
+  }
+  return c;
+}
+
+StencilCoef make_stencil_coef(const double spacing[3]) {
+  StencilCoef s;
+  for (int d = 0; d < 3; ++d) {
+    const double inv = 1.0 / spacing[d];
+    s.d1[d] = (double)(float)(0.5 * inv);
+    s.d2a[d] = (double)(float)(1.0 * inv);
+    s.d2b[d] = (double)(float)(-2.0 * inv);
+    s.g1[d] = 0.5 * inv;
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Recursive Gaussian passes
+// ---------------------------------------------------------------------------------------
+constexpr int kChunk = 16;
+constexpr int kXWarps = 4;
+
+size_t ckpt_bytes(int nf, int n, size_t n_lines) {
+  const int n_chunks = (n + kChunk - 1) / kChunk;
+  return (size_t)std::max(n_chunks - 1, 0) * nf * 4 * n_lines * sizeof(double);
+}
+
+size_t ckpt_bytes_volume(int nf, int nx, int ny, int nz) {
+  const size_t a = ckpt_bytes(nf, nz, (size_t)nx * ny);
+  const size_t b = ckpt_bytes(nf, nx, (size_t)ny * nz);
+  const size_t c = ckpt_bytes(nf, ny, (size_t)nx * nz);
+  return std::max(a, std::max(b, c));
+}
+
+template <int NF, int INMODE, bool DIVIDE>
+int launch_strided(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
+  const unsigned grid = (unsigned)((A.n_lines + 127) / 128);
+  if (ctx->arith == IFE_ARITH_FMA)
+    gauss_pass_strided<NF, INMODE, DIVIDE, kChunk, true><<<grid, 128, 0, ctx->stream()>>>(C, A);
+  else
+    gauss_pass_strided<NF, INMODE, DIVIDE, kChunk, false><<<grid, 128, 0, ctx->stream()>>>(C, A);
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
+template <int NF>
+int launch_x(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
+  const long long lines_per_block = 32LL * kXWarps;
+  const unsigned grid = (unsigned)((A.n_lines + lines_per_block - 1) / lines_per_block);
+  if (ctx->arith == IFE_ARITH_FMA)
+    gauss_pass_x<NF, kChunk, true, kXWarps><<<grid, 32 * kXWarps, 0, ctx->stream()>>>(C, A);
+  else
+    gauss_pass_x<NF, kChunk, false, kXWarps><<<grid, 32 * kXWarps, 0, ctx->stream()>>>(C, A);
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
+// Smooth `nzb` planes of nx*ny.  Pass order z, x, y as SmoothingRecursiveGaussianImageFilter.
+//   nf == 1: out0 = G(in0)                                       (in1 unused)
+//   nf == 2: fields (in0*c, c) with c = in1 (u8 or f32); result = G(in0*c)/G(c) -> out0
+// The z pass runs over all nzb planes; the x and y passes (which do not couple planes) only
+// over planes [keep0, keep1), and out0 / outmask_* hold exactly those planes (a z-slab
+// keeps its owned planes +-1 and drops the warm-up halo after the z pass).
+// Scratch: ws.a0,a1,b0,b1 and ws.ckpt must already be large enough.
+int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool cert_is_u8,
+                  float* out0, int nx, int ny, int nzb, int keep0, int keep1,
+                  const double spacing[3], double sigma, const uint8_t* outmask_u8,
+                  const float* outmask_f32) {
+  if (nx < 4 || ny < 4 || nzb < 4)
+    return fail(ctx, IFE_E_TOO_SMALL,
+                "recursive Gaussian needs at least 4 samples per axis (got %d x %d x %d)", nx, ny,
+                nzb);
+  if (!(sigma > 0.0)) return fail(ctx, IFE_E_INVALID, "sigma must be positive (got %g)", sigma);
+  if (keep0 < 0 || keep1 > nzb || keep0 >= keep1) return fail(ctx, IFE_E_INVALID, "bad plane range");
+  const int nf = cert ? 2 : 1;
+  Workspace& ws = ctx->ws;
+  const GaussCoef cz = make_gauss_coef(sigma, spacing[2]);
+  const GaussCoef cx = make_gauss_coef(sigma, spacing[0]);
+  const GaussCoef cy = make_gauss_coef(sigma, spacing[1]);
+  float* a0 = (float*)ws.a0.ptr;
+  float* a1 = (float*)ws.a1.ptr;
+  float* b0 = (float*)ws.b0.ptr;
+  float* b1 = (float*)ws.b1.ptr;
+
+  PassArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.ckpt = (double*)ws.ckpt.ptr;
+
+  // z pass: lines = nx*ny columns, contiguous across the plane
+  A.in0 = in0; A.in1 = cert; A.out0 = a0; A.out1 = a1;
+  A.n = nzb; A.stride = (long long)nx * ny; A.na = nx * ny > 0 ? nx * ny : 1; A.sb = 0;
+  A.n_lines = (long long)nx * ny;
+  if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cz, A)));
+  else if (cert_is_u8) IFE_TRY((launch_strided<2, IN_IMG_U8, false>(ctx, cz, A)));
+  else IFE_TRY((launch_strided<2, IN_IMG_F32, false>(ctx, cz, A)));
+
+  // x pass: lines = ny*nzk rows, contiguous
+  const int nzk = keep1 - keep0;
+  const size_t koff = (size_t)keep0 * nx * ny;
+  A.in0 = a0 + koff; A.in1 = a1 + koff; A.out0 = b0; A.out1 = b1;
+  A.n = nx; A.stride = 1; A.na = 1; A.sb = 0; A.n_lines = (long long)ny * nzk;
+  if (nf == 1) IFE_TRY((launch_x<1>(ctx, cx, A)));
+  else IFE_TRY((launch_x<2>(ctx, cx, A)));
+
+  // y pass: lines indexed (x, z); base = x + z*nx*ny; stride nx
+  A.in0 = b0; A.in1 = b1; A.out0 = out0; A.out1 = nullptr;
+  A.n = ny; A.stride = nx; A.na = nx; A.sb = (long long)nx * ny; A.n_lines = (long long)nx * nzk;
+  A.mask_u8 = outmask_u8; A.mask_f32 = outmask_f32;
+  if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cy, A)));
+  else IFE_TRY((launch_strided<2, IN_FIELDS, true>(ctx, cy, A)));
+  return IFE_OK;
+}
+
+int reserve_smoothing(ife_cuda_ctx* ctx, int nf, int nx, int ny, int nzb) {
+  Workspace& ws = ctx->ws;
+  const size_t vol = (size_t)nx * ny * nzb * sizeof(float);
+  IFE_TRY(ws.a0.reserve(ctx, vol));
+  IFE_TRY(ws.b0.reserve(ctx, vol));
+  if (nf == 2) {
+    IFE_TRY(ws.a1.reserve(ctx, vol));
+    IFE_TRY(ws.b1.reserve(ctx, vol));
+  }
+  IFE_TRY(ws.ckpt.reserve(ctx, std::max<size_t>(ckpt_bytes_volume(nf, nx, ny, nzb), 8)));
+  return IFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused feature kernel launch
+// ---------------------------------------------------------------------------------------
+int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const FeatArgs& A) {
+  const bool hist = A.hist.edges != nullptr;
+  const int nfeat = mode == 0 ? 8 : (mode == 1 ? 6 : 1);
+  const size_t n_out = (size_t)A.nx * A.ny * (size_t)(A.zb1 - A.zb0);
+  if (n_out == 0) return IFE_OK;
+  const int block = 256;
+  const size_t want = (n_out + block - 1) / block;
+  const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * 32);
+  const size_t smem =
+      hist ? (size_t)nfeat * (A.hist.n_edges * sizeof(float) + (A.hist.n_edges + 1) * sizeof(uint32_t))
+           : 0;
+  if (smem > 48 * 1024)
+    return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d) for shared memory", A.hist.n_edges);
+  cudaStream_t st = ctx->stream();
+  if (mode == 0) {
+    if (hist) features_kernel<0, true><<<grid, block, smem, st>>>(S, A);
+    else features_kernel<0, false><<<grid, block, 0, st>>>(S, A);
+  } else if (mode == 1) {
+    if (hist) features_kernel<1, true><<<grid, block, smem, st>>>(S, A);
+    else features_kernel<1, false><<<grid, block, 0, st>>>(S, A);
+  } else {
+    if (hist) features_kernel<2, true><<<grid, block, smem, st>>>(S, A);
+    else features_kernel<2, false><<<grid, block, 0, st>>>(S, A);
+  }
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
+int check_dims(ife_cuda_ctx* ctx, const int dims[3], const double spacing[3]) {
+  if (!dims || !spacing) return fail(ctx, IFE_E_INVALID, "dims/spacing must not be null");
+  for (int d = 0; d < 3; ++d) {
+    if (dims[d] <= 0) return fail(ctx, IFE_E_INVALID, "dims[%d] = %d must be positive", d, dims[d]);
+    if (!(spacing[d] > 0.0))
+      return fail(ctx, IFE_E_INVALID, "spacing[%d] = %g must be positive", d, spacing[d]);
+  }
+  return IFE_OK;
+}
+
+// Stage a host array on the device (or pass a device pointer through).
+template <typename T>
+int stage_in(ife_cuda_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, int mem,
+             const T** dev) {
+  if (!src) { *dev = nullptr; return IFE_OK; }
+  if (mem == IFE_MEM_DEVICE) { *dev = src; return IFE_OK; }
+  IFE_TRY(buf.reserve(ctx, count * sizeof(T)));
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(buf.ptr, src, count * sizeof(T), cudaMemcpyHostToDevice,
+                                    ctx->stream()));
+  *dev = (const T*)buf.ptr;
+  return IFE_OK;
+}
+
+}  // namespace ife
+
+using namespace ife;
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+int ife_cuda_abi_version(void) { return IFE_CUDA_ABI_VERSION; }
+
+int ife_cuda_create(int device, ife_cuda_ctx** out) {
+  if (!out) return IFE_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return IFE_E_CUDA;
+  ife_cuda_ctx* ctx = new ife_cuda_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return IFE_E_CUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  for (auto& ev : ctx->events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  *out = ctx;
+  return IFE_OK;
+}
+
+void ife_cuda_destroy(ife_cuda_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ife_cuda_comm_destroy(ctx);
+  ctx->ws.release_all();
+  for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* ife_cuda_last_error(const ife_cuda_ctx* ctx) {
+  return ctx ? ctx->error.c_str() : "null context";
+}
+
+int ife_cuda_set_stream(ife_cuda_ctx* ctx, void* s) {
+  if (!ctx) return IFE_E_INVALID;
+  ctx->user_stream = (cudaStream_t)s;
+  ctx->use_user_stream = s != nullptr;
+  return IFE_OK;
+}
+
+int ife_cuda_set_arith(ife_cuda_ctx* ctx, int mode) {
+  if (!ctx) return IFE_E_INVALID;
+  if (mode != IFE_ARITH_PLAIN && mode != IFE_ARITH_FMA)
+    return fail(ctx, IFE_E_INVALID, "unknown arithmetic mode %d", mode);
+  ctx->arith = mode;
+  return IFE_OK;
+}
+
+int ife_cuda_get_arith(const ife_cuda_ctx* ctx) { return ctx ? ctx->arith : IFE_E_INVALID; }
+
+int ife_cuda_synchronize(ife_cuda_ctx* ctx) {
+  if (!ctx) return IFE_E_INVALID;
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return IFE_OK;
+}
+
+uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ife_cuda_reserve(ife_cuda_ctx* ctx, const int dims[3], int n_outputs) {
+  if (!ctx || !dims) return IFE_E_INVALID;
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  IFE_TRY(reserve_smoothing(ctx, 2, dims[0], dims[1], dims[2]));
+  IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
+  if (n_outputs > 0) {
+    IFE_TRY(ctx->ws.in_img.reserve(ctx, n * sizeof(float)));
+    IFE_TRY(ctx->ws.in_mask.reserve(ctx, n * sizeof(float)));
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, n * sizeof(float) * n_outputs));
+    if (n_outputs >= 8) IFE_TRY(ctx->ws.out[1].reserve(ctx, n * sizeof(float) * n_outputs));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_gaussian(ife_cuda_ctx* ctx, const float* in, float* out, const int dims[3],
+                      const double spacing[3], double sigma, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!in || !out) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  IFE_TRY(reserve_smoothing(ctx, 1, dims[0], dims[1], dims[2]));
+  const float* d_in;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, in, n, mem, &d_in));
+  float* d_out = out;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, n * sizeof(float)));
+    d_out = (float*)ctx->ws.out[0].ptr;
+  }
+  IFE_TRY(smooth_volume(ctx, d_in, nullptr, false, d_out, dims[0], dims[1], dims[2], 0, dims[2], spacing,
+                        sigma, nullptr, nullptr));
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_normalized_gaussian(ife_cuda_ctx* ctx, const float* image, const float* cert_f32,
+                                 const uint8_t* cert_u8, float* out, const int dims[3],
+                                 const double spacing[3], double sigma, int mask_output, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !out) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  if ((cert_f32 == nullptr) == (cert_u8 == nullptr))
+    return fail(ctx, IFE_E_INVALID, "exactly one of certainty_f32 / certainty_u8 must be given");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  IFE_TRY(reserve_smoothing(ctx, 2, dims[0], dims[1], dims[2]));
+  const float* d_img;
+  const float* d_cf = nullptr;
+  const uint8_t* d_cu = nullptr;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  if (cert_f32) IFE_TRY(stage_in(ctx, ctx->ws.in_mask, cert_f32, n, mem, &d_cf));
+  else IFE_TRY(stage_in(ctx, ctx->ws.in_mask, cert_u8, n, mem, &d_cu));
+  float* d_out = out;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, n * sizeof(float)));
+    d_out = (float*)ctx->ws.out[0].ptr;
+  }
+  const void* cert = cert_f32 ? (const void*)d_cf : (const void*)d_cu;
+  IFE_TRY(smooth_volume(ctx, d_img, cert, cert_u8 != nullptr, d_out, dims[0], dims[1], dims[2],
+                        0, dims[2], spacing, sigma, mask_output ? d_cu : nullptr,
+                        mask_output ? d_cf : nullptr));
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_gradient_magnitude(ife_cuda_ctx* ctx, const float* in, const float* mask_f32,
+                                const uint8_t* mask_u8, float* out, const int dims[3],
+                                const double spacing[3], int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!in || !out) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  const float* d_in;
+  const float* d_mf = nullptr;
+  const uint8_t* d_mu = nullptr;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, in, n, mem, &d_in));
+  if (mask_f32) IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask_f32, n, mem, &d_mf));
+  else if (mask_u8) IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask_u8, n, mem, &d_mu));
+  float* d_out = out;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, n * sizeof(float)));
+    d_out = (float*)ctx->ws.out[0].ptr;
+  }
+  FeatArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.vol = d_in; A.mask_u8 = d_mu; A.mask_f32 = d_mf; A.out[0] = d_out;
+  A.nx = dims[0]; A.ny = dims[1]; A.nzb = dims[2]; A.zb0 = 0; A.zb1 = dims[2];
+  IFE_TRY(launch_features(ctx, 2, make_stencil_coef(spacing), A));
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_hessian_eigen_features(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                    float* out6, const int dims[3], const double spacing[3],
+                                    double sigma, int flags, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !out6) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  const float* d_img;
+  const uint8_t* d_mask;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
+  const float* src = d_img;
+  if (sigma > 0.0) {
+    IFE_TRY(reserve_smoothing(ctx, 1, dims[0], dims[1], dims[2]));
+    IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
+    IFE_TRY(smooth_volume(ctx, d_img, nullptr, false, (float*)ctx->ws.blur.ptr, dims[0], dims[1],
+                          dims[2], 0, dims[2], spacing, sigma, nullptr, nullptr));
+    src = (const float*)ctx->ws.blur.ptr;
+  }
+  float* d_out = out6;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, 6 * n * sizeof(float)));
+    d_out = (float*)ctx->ws.out[0].ptr;
+  }
+  FeatArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.vol = src; A.mask_u8 = d_mask;
+  for (int k = 0; k < 6; ++k) A.out[k] = d_out + (size_t)k * n;
+  A.nx = dims[0]; A.ny = dims[1]; A.nzb = dims[2]; A.zb0 = 0; A.zb1 = dims[2];
+  A.dy_bug = (flags & IFE_FDHF_TOOL_DY_BUG) ? 1 : 0;
+  IFE_TRY(launch_features(ctx, 1, make_stencil_coef(spacing), A));
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out6, d_out, 6 * n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                float* out, const int dims[3], const double spacing[3],
+                                const double* sigmas, int n_sigma, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !mask || !out) return fail(ctx, IFE_E_INVALID, "null image/mask/out pointer");
+  if (!sigmas || n_sigma <= 0) return fail(ctx, IFE_E_INVALID, "need at least one scale");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int nx = dims[0], ny = dims[1], nz = dims[2];
+  const size_t n = (size_t)nx * ny * nz;
+  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nz));
+  IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
+  const float* d_img;
+  const uint8_t* d_mask;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
+  if (mem == IFE_MEM_HOST) {
+    // two staging buffers so that the D2H copy of scale s overlaps the kernels of scale s+1
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, 8 * n * sizeof(float)));
+    if (n_sigma > 1) IFE_TRY(ctx->ws.out[1].reserve(ctx, 8 * n * sizeof(float)));
+  }
+  const StencilCoef S = make_stencil_coef(spacing);
+  for (int s = 0; s < n_sigma; ++s) {
+    float* blur = (float*)ctx->ws.blur.ptr;
+    float* d_out = mem == IFE_MEM_HOST ? (float*)ctx->ws.out[s & 1].ptr : out + (size_t)s * 8 * n;
+    if (mem == IFE_MEM_HOST && s >= 2)  // the staging buffer must have been drained
+      IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream(), ctx->events[2 + (s & 1)], 0));
+    IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
+                          nullptr, nullptr));
+    FeatArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.vol = blur; A.mask_u8 = d_mask;
+    for (int k = 0; k < 8; ++k) A.out[k] = d_out + (size_t)k * n;
+    A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
+    IFE_TRY(launch_features(ctx, 0, S, A));
+    if (mem == IFE_MEM_HOST) {
+      IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[s & 1], ctx->stream()));
+      IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[s & 1], 0));
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n, d_out, 8 * n * sizeof(float),
+                                        cudaMemcpyDeviceToHost, ctx->copy_stream));
+      IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[2 + (s & 1)], ctx->copy_stream));
+    }
+  }
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                  const int dims[3], const double spacing[3], const double* sigmas,
+                                  int n_sigma, const float* edges, int n_edges, const int* rois,
+                                  int n_roi, uint32_t* counts, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !mask || !counts || !edges) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  if (!sigmas || n_sigma <= 0) return fail(ctx, IFE_E_INVALID, "need at least one scale");
+  if (n_edges <= 0) return fail(ctx, IFE_E_INVALID, "need at least one histogram edge");
+  if (n_roi < 0 || (n_roi > 0 && !rois)) return fail(ctx, IFE_E_INVALID, "bad ROI list");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int nx = dims[0], ny = dims[1], nz = dims[2];
+  const size_t n = (size_t)nx * ny * nz;
+  for (int r = 0; r < n_roi; ++r) {
+    const int* b = rois + 6 * r;
+    if (b[0] < 0 || b[1] < 0 || b[2] < 0 || b[3] <= 0 || b[4] <= 0 || b[5] <= 0 ||
+        b[0] + b[3] > nx || b[1] + b[4] > ny || b[2] + b[5] > nz)
+      return fail(ctx, IFE_E_INVALID, "ROI %d is not inside the image", r);
+  }
+  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nz));
+  IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
+  const float* d_img;
+  const uint8_t* d_mask;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
+
+  const int rows = n_sigma * 8, nb = n_edges + 1, R = std::max(n_roi, 1);
+  const size_t n_counts = (size_t)R * rows * nb;
+  // parameter arrays are host pointers; counts follows `mem`
+  IFE_TRY(ctx->ws.edges.reserve(ctx, (size_t)rows * n_edges * sizeof(float)));
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.edges.ptr, edges, (size_t)rows * n_edges * sizeof(float),
+                                    cudaMemcpyHostToDevice, ctx->stream()));
+  const int* d_rois = nullptr;
+  if (n_roi > 0) {
+    IFE_TRY(ctx->ws.rois.reserve(ctx, (size_t)n_roi * 6 * sizeof(int)));
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.rois.ptr, rois, (size_t)n_roi * 6 * sizeof(int),
+                                      cudaMemcpyHostToDevice, ctx->stream()));
+    d_rois = (const int*)ctx->ws.rois.ptr;
+  }
+  uint32_t* d_counts = counts;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.counts.reserve(ctx, n_counts * sizeof(uint32_t)));
+    d_counts = (uint32_t*)ctx->ws.counts.ptr;
+  }
+  IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), ctx->stream()));
+
+  const StencilCoef S = make_stencil_coef(spacing);
+  for (int s = 0; s < n_sigma; ++s) {
+    float* blur = (float*)ctx->ws.blur.ptr;
+    IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
+                          nullptr, nullptr));
+    FeatArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.vol = blur; A.mask_u8 = d_mask;
+    A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
+    A.hist.edges = (const float*)ctx->ws.edges.ptr + (size_t)s * 8 * n_edges;
+    A.hist.counts = d_counts + (size_t)s * 8 * nb;
+    A.hist.rois = d_rois; A.hist.n_roi = n_roi; A.hist.n_edges = n_edges;
+    A.hist.stride_roi = (long long)rows * nb;
+    IFE_TRY(launch_features(ctx, 0, S, A));
+  }
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, n_counts * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const float* edges,
+                       int n_edges, uint32_t* counts, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!edges || !counts || (n > 0 && !values)) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  if (n_edges <= 0) return fail(ctx, IFE_E_INVALID, "need at least one histogram edge");
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t smem = n_edges * sizeof(float) + (n_edges + 1) * sizeof(uint32_t);
+  if (smem > 48 * 1024) return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d)", n_edges);
+  const float* d_vals = nullptr;
+  if (n > 0) IFE_TRY(stage_in(ctx, ctx->ws.in_img, values, n, mem, &d_vals));
+  IFE_TRY(ctx->ws.edges.reserve(ctx, n_edges * sizeof(float)));
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.edges.ptr, edges, n_edges * sizeof(float),
+                                    cudaMemcpyHostToDevice, ctx->stream()));
+  uint32_t* d_counts = counts;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.counts.reserve(ctx, (n_edges + 1) * sizeof(uint32_t)));
+    d_counts = (uint32_t*)ctx->ws.counts.ptr;
+  }
+  IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (n_edges + 1) * sizeof(uint32_t), ctx->stream()));
+  if (n > 0) {
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+    histogram_kernel<<<grid, 256, smem, ctx->stream()>>>(d_vals, n, (const float*)ctx->ws.edges.ptr,
+                                                         n_edges, d_counts);
+    ctx->launches++;
+    IFE_CUDA_TRY(ctx, cudaGetLastError());
+  }
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, (n_edges + 1) * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_eigen_features_batch(ife_cuda_ctx* ctx, const float* A6, float* out6, size_t n,
+                                  int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (n == 0) return IFE_OK;
+  if (!A6 || !out6) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const float* d_in;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, A6, 6 * n, mem, &d_in));
+  float* d_out = out6;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, 6 * n * sizeof(float)));
+    d_out = (float*)ctx->ws.out[0].ptr;
+  }
+  eigen_features_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream()>>>(d_in, d_out, n);
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out6, d_out, 6 * n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+}  // extern "C"
+
+#include "slab.cuh"

@@ -1,0 +1,258 @@
+// Multi-GPU z-slab path: halo exchange over NCCL send/recv, per-rank pipeline on
+// slab+halo, histogram all-reduce.  Included by ife_cuda.cu (single translation unit).
+//
+// The reference has nothing distributed (single process, whole volume in host RAM,
+// `UpdateLargestPossibleRegion()` everywhere: tools/ExtractFeatures.cxx:142); this is the
+// B200 answer to volumes that want more than one GPU.  The volume is cut into contiguous
+// z-slabs (z is the slowest index, so a slab is one contiguous block).  The only stage
+// that couples planes beyond +-1 is the z pass of the recursive Gaussian, an IIR whose
+// response to a wrong start state decays as exp(-1.37 d/sigma): each rank therefore
+// receives H = ceil(halo_factor*sigma_max/spacing_z)+5 raw planes from its z neighbours
+// ONCE per call (image 4 B/voxel + mask 1 B/voxel, grouped ncclSend/ncclRecv over
+// NVLink), runs the z pass on slab+halo, and everything after it on slab+-1 planes.
+// Global volume edges use the filter's own boundary rule, so a 1-rank run is identical to
+// the single-GPU entry point.
+//
+// NCCL is bound lazily with dlopen so that single-GPU users need no NCCL at all.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace ife {
+
+struct NcclApi {
+  void* handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+
+inline NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.handle) return api;
+  // a process that already loaded an NCCL (e.g. torch's bundled one) gets that one
+  api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.handle) return api;
+#define IFE_NCCL_SYM(name) api.name = (decltype(api.name))dlsym(api.handle, "nccl" #name)
+  IFE_NCCL_SYM(GetUniqueId);
+  IFE_NCCL_SYM(CommInitRank);
+  IFE_NCCL_SYM(CommDestroy);
+  IFE_NCCL_SYM(Send);
+  IFE_NCCL_SYM(Recv);
+  IFE_NCCL_SYM(AllReduce);
+  IFE_NCCL_SYM(GroupStart);
+  IFE_NCCL_SYM(GroupEnd);
+  IFE_NCCL_SYM(GetErrorString);
+#undef IFE_NCCL_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv &&
+           api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString;
+  return api;
+}
+
+#define IFE_NCCL_TRY(ctx, expr)                                                           \
+  do {                                                                                    \
+    ncclResult_t r_ = (expr);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      return ife::fail(ctx, IFE_E_COMM, "%s failed: %s", #expr, nccl_api().GetErrorString(r_)); \
+  } while (0)
+
+inline void slab_range(int nz, int n_ranks, int rank, int* z0, int* z1) {
+  *z0 = (int)((long long)nz * rank / n_ranks);
+  *z1 = (int)((long long)nz * (rank + 1) / n_ranks);
+}
+
+}  // namespace ife
+
+extern "C" {
+
+int ife_cuda_comm_unique_id(ife_cuda_ctx* ctx, uint8_t id[IFE_COMM_ID_BYTES]) {
+  if (!ctx || !id) return IFE_E_INVALID;
+  ife::NcclApi& api = ife::nccl_api();
+  if (!api.ok) return ife::fail(ctx, IFE_E_COMM, "libnccl.so.2 could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == IFE_COMM_ID_BYTES, "NCCL unique id size");
+  ncclUniqueId uid;
+  IFE_NCCL_TRY(ctx, api.GetUniqueId(&uid));
+  std::memcpy(id, &uid, sizeof(uid));
+  return IFE_OK;
+}
+
+int ife_cuda_comm_init(ife_cuda_ctx* ctx, const uint8_t id[IFE_COMM_ID_BYTES], int n_ranks,
+                       int rank) {
+  if (!ctx || !id) return IFE_E_INVALID;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
+    return ife::fail(ctx, IFE_E_INVALID, "bad rank %d of %d", rank, n_ranks);
+  ife::NcclApi& api = ife::nccl_api();
+  if (!api.ok) return ife::fail(ctx, IFE_E_COMM, "libnccl.so.2 could not be loaded");
+  if (ctx->nccl_comm) ife_cuda_comm_destroy(ctx);
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclComm_t comm;
+  IFE_NCCL_TRY(ctx, api.CommInitRank(&comm, n_ranks, uid, rank));
+  ctx->nccl_comm = comm;
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return IFE_OK;
+}
+
+int ife_cuda_comm_destroy(ife_cuda_ctx* ctx) {
+  if (!ctx) return IFE_E_INVALID;
+  if (ctx->nccl_comm) {
+    ife::nccl_api().CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  ctx->n_ranks = 1;
+  ctx->rank = 0;
+  return IFE_OK;
+}
+
+void ife_cuda_slab_range(int nz_global, int n_ranks, int rank, int* z0, int* z1) {
+  ife::slab_range(nz_global, n_ranks, rank, z0, z1);
+}
+
+int ife_cuda_slab_halo(double sigma, double spacing_z, double halo_factor) {
+  if (!(halo_factor > 0.0)) halo_factor = 12.0;
+  return (int)std::ceil(halo_factor * sigma / spacing_z) + 4 + 1;
+}
+
+int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
+                                     const uint8_t* mask_slab, float* out,
+                                     const int global_dims[3], const double spacing[3],
+                                     const double* sigmas, int n_sigma, const float* edges,
+                                     int n_edges, uint32_t* counts, double halo_factor, int mem) {
+  using namespace ife;
+  if (!ctx) return IFE_E_INVALID;
+  if (!image_slab) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  if (!out && !edges) return fail(ctx, IFE_E_INVALID, "nothing to compute: out and edges both null");
+  if (edges && (!counts || n_edges <= 0)) return fail(ctx, IFE_E_INVALID, "bad histogram arguments");
+  if (!sigmas || n_sigma <= 0) return fail(ctx, IFE_E_INVALID, "need at least one scale");
+  IFE_TRY(check_dims(ctx, global_dims, spacing));
+  const int P = ctx->n_ranks, me = ctx->rank;
+  if (P > 1 && !ctx->nccl_comm) return fail(ctx, IFE_E_COMM, "communicator not initialised");
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NcclApi& api = nccl_api();
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  cudaStream_t st = ctx->stream();
+
+  const int nx = global_dims[0], ny = global_dims[1], nz = global_dims[2];
+  const size_t plane = (size_t)nx * ny;
+  int z0, z1;
+  slab_range(nz, P, me, &z0, &z1);
+  const int nzo = z1 - z0;
+  if (nzo <= 0) return fail(ctx, IFE_E_INVALID, "rank %d owns no planes (nz=%d, ranks=%d)", me, nz, P);
+  double smax = 0.0;
+  for (int s = 0; s < n_sigma; ++s) smax = std::max(smax, sigmas[s]);
+  const int Hmax = ife_cuda_slab_halo(smax, spacing[2], halo_factor);
+  const int bz0 = std::max(0, z0 - Hmax), bz1 = std::min(nz, z1 + Hmax);
+  const int nzb = bz1 - bz0;
+  const size_t n_own = plane * nzo;
+
+  // ---- slab + halo buffers ----
+  Workspace& ws = ctx->ws;
+  IFE_TRY(ws.slab_img.reserve(ctx, plane * nzb * sizeof(float)));
+  IFE_TRY(ws.slab_mask.reserve(ctx, plane * nzb));
+  float* bimg = (float*)ws.slab_img.ptr;
+  uint8_t* bmask = (uint8_t*)ws.slab_mask.ptr;
+  const cudaMemcpyKind kin = mem == IFE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(bimg + plane * (z0 - bz0), image_slab, n_own * sizeof(float), kin, st));
+  if (mask_slab)
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(bmask + plane * (z0 - bz0), mask_slab, n_own, kin, st));
+  else
+    IFE_CUDA_TRY(ctx, cudaMemsetAsync(bmask + plane * (z0 - bz0), 1, n_own, st));
+
+  // ---- halo exchange: every pair of ranks whose (slab+halo) and slab overlap ----
+  if (P > 1) {
+    IFE_NCCL_TRY(ctx, api.GroupStart());
+    for (int r = 0; r < P; ++r) {
+      if (r == me) continue;
+      int rz0, rz1;
+      slab_range(nz, P, r, &rz0, &rz1);
+      // planes I need from r: [bz0,bz1) minus my own, intersected with r's slab
+      const int n0 = std::max(bz0, rz0), n1 = std::min(bz1, rz1);
+      if (n0 < n1) {
+        IFE_NCCL_TRY(ctx, api.Recv(bimg + plane * (n0 - bz0), plane * (n1 - n0), ncclFloat, r, comm, st));
+        IFE_NCCL_TRY(ctx, api.Recv(bmask + plane * (n0 - bz0), plane * (n1 - n0), ncclUint8, r, comm, st));
+      }
+      // planes r needs from me (same Hmax on every rank)
+      const int rb0 = std::max(0, rz0 - Hmax), rb1 = std::min(nz, rz1 + Hmax);
+      const int s0 = std::max(rb0, z0), s1 = std::min(rb1, z1);
+      if (s0 < s1) {
+        IFE_NCCL_TRY(ctx, api.Send(bimg + plane * (s0 - bz0), plane * (s1 - s0), ncclFloat, r, comm, st));
+        IFE_NCCL_TRY(ctx, api.Send(bmask + plane * (s0 - bz0), plane * (s1 - s0), ncclUint8, r, comm, st));
+      }
+    }
+    IFE_NCCL_TRY(ctx, api.GroupEnd());
+  }
+
+  // ---- per-scale pipeline ----
+  const int fz0 = std::max(0, z0 - 1), fz1 = std::min(nz, z1 + 1);  // planes the stencil reads
+  const int nzf = fz1 - fz0;
+  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nzb));
+  IFE_TRY(ws.blur.reserve(ctx, plane * nzf * sizeof(float)));
+  const int rows = n_sigma * 8, nb = n_edges + 1;
+  uint32_t* d_counts = nullptr;
+  if (edges) {
+    IFE_TRY(ws.edges.reserve(ctx, (size_t)rows * n_edges * sizeof(float)));
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ws.edges.ptr, edges, (size_t)rows * n_edges * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+    if (mem == IFE_MEM_HOST) {
+      IFE_TRY(ws.counts.reserve(ctx, (size_t)rows * nb * sizeof(uint32_t)));
+      d_counts = (uint32_t*)ws.counts.ptr;
+    } else {
+      d_counts = counts;
+    }
+    IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)rows * nb * sizeof(uint32_t), st));
+  }
+  if (out && mem == IFE_MEM_HOST) IFE_TRY(ws.out[0].reserve(ctx, 8 * n_own * sizeof(float)));
+
+  const StencilCoef S = make_stencil_coef(spacing);
+  for (int s = 0; s < n_sigma; ++s) {
+    const int H = ife_cuda_slab_halo(sigmas[s], spacing[2], halo_factor);
+    const int sz0 = std::max(0, z0 - H), sz1 = std::min(nz, z1 + H);  // z-pass extent at this scale
+    float* blur = (float*)ws.blur.ptr;
+    IFE_TRY(smooth_volume(ctx, bimg + plane * (sz0 - bz0), bmask + plane * (sz0 - bz0), true, blur, nx,
+                          ny, sz1 - sz0, fz0 - sz0, fz1 - sz0, spacing, sigmas[s], nullptr, nullptr));
+    FeatArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.vol = blur;
+    A.mask_u8 = bmask + plane * (fz0 - bz0);
+    A.nx = nx; A.ny = ny; A.nzb = nzf; A.zb0 = z0 - fz0; A.zb1 = A.zb0 + nzo; A.z_global0 = fz0;
+    float* d_out = nullptr;
+    if (out) {
+      d_out = mem == IFE_MEM_HOST ? (float*)ws.out[0].ptr : out + (size_t)s * 8 * n_own;
+      for (int k = 0; k < 8; ++k) A.out[k] = d_out + (size_t)k * n_own;
+    }
+    if (edges) {
+      A.hist.edges = (const float*)ws.edges.ptr + (size_t)s * 8 * n_edges;
+      A.hist.counts = d_counts + (size_t)s * 8 * nb;
+      A.hist.n_edges = n_edges;
+      A.hist.n_roi = 0;
+      A.hist.stride_roi = (long long)rows * nb;
+    }
+    IFE_TRY(launch_features(ctx, 0, S, A));
+    if (out && mem == IFE_MEM_HOST)
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n_own, d_out, 8 * n_own * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+  }
+
+  // ---- combine the per-rank histograms ----
+  if (edges) {
+    if (P > 1)
+      IFE_NCCL_TRY(ctx, api.AllReduce(d_counts, d_counts, (size_t)rows * nb, ncclUint32, ncclSum, comm, st));
+    if (mem == IFE_MEM_HOST)
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)rows * nb * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, st));
+  }
+  if (mem == IFE_MEM_HOST) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return IFE_OK;
+}
+
+}  // extern "C"

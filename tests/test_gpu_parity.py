@@ -1,0 +1,319 @@
+"""GPU parity tests: the CUDA path, called through the C ABI with host buffers, against the
+CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): eigenvalues within 1e-4 * max|lambda| per voxel with the
+same ordering; histogram counts exact except for voxels within that tolerance of an edge.
+What is asserted here is stronger: every stage is BIT-IDENTICAL to the oracle run in the
+same arithmetic mode, except that the solver's double-precision acos/cos come from CUDA's
+libdevice instead of glibc, which after narrowing to float may flip the last bit of an
+eigenvalue for a vanishing fraction of voxels (<= MISMATCH_FRAC, each still within TOL).
+"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4            # relative to max|lambda| per voxel (north_star)
+MISMATCH_FRAC = 2e-5  # allowed fraction of last-bit differences from libm vs libdevice
+
+
+def bits_equal(a, b):
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def mismatch_report(gpu, ref):
+    """(#elements that differ, max |diff|) with NaN == NaN and -0 == +0."""
+    neq = ~((gpu == ref) | (np.isnan(gpu) & np.isnan(ref)))
+    n = int(neq.sum())
+    return n, (float(np.max(np.abs(gpu[neq].astype(np.float64) - ref[neq]))) if n else 0.0)
+
+
+def assert_eigen_parity(gpu6, ref6, what):
+    """gpu6/ref6: (..., 6) features [e1,e2,e3,LoG,Curv,Frob]."""
+    g = gpu6.reshape(-1, 6); r = ref6.reshape(-1, 6)
+    finite = np.isfinite(r).all(1)
+    assert np.array_equal(np.isnan(g), np.isnan(r)), what
+    neq_rows = (~((g == r) | (np.isnan(g) & np.isnan(r)))).any(1)
+    frac = neq_rows.mean()
+    assert frac <= MISMATCH_FRAC, "%s: %.3g of voxels differ" % (what, frac)
+    rows = neq_rows & finite
+    if rows.any():
+        lam = np.abs(r[rows, :3]).max(1)
+        err = np.abs(g[rows, :3].astype(np.float64) - r[rows, :3]).max(1)
+        assert np.all(err <= TOL * lam), "%s: eigenvalue error beyond 1e-4*max|lambda|" % what
+
+
+# ------------------------------------------------------------------------------ solver
+def test_solver_batch_matches_reference_golden(ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "solver_ref.npz"))
+    out = ctx.eigen_features_batch(g["A6"])
+    assert_eigen_parity(out, g["features_f32"], "golden")
+    # diagonal / tie cases never touch a transcendental: exactly equal
+    diag = (g["A6"][:, [1, 2, 4]] == 0).all(1)
+    assert bits_equal(out[diag], g["features_f32"][diag])
+
+
+def test_solver_batch_matches_oracle_2M(ctx, oracle):
+    A = synth.special_matrices(2_000_000, seed=21)
+    out = ctx.eigen_features_batch(A)
+    ref = oracle.features_f32(A)
+    assert_eigen_parity(out, ref, "2M sweep")
+    n, _ = mismatch_report(out, ref)
+    print("solver sweep: %d of %d values differ from the oracle" % (n, out.size))
+    # the reference's own known answers (test/Symmetric3x3EigenvalueSolverTest.cxx:48-90)
+    kat = np.array([[1, 0, 0, 1, 0, 1], [1, 0, 0, 2, 0, 3], [-1, 0, 0, -2, 0, -3], [1, 0, 0, -2, 0, 3],
+                    [0.27, 0.92, 0.58, 0.24, 0.75, 0.04], [599, 860, -835, -941, 817, -207]], np.float32)
+    exp = np.array([[1, 1, 1], [3, 2, 1], [-3, -2, -1], [3, -2, 1],
+                    [1.70680634, -0.7205504, -0.43625594], [-2005.21004566, 1183.41690727, 272.79313839]])
+    got = ctx.eigen_features_batch(kat)[:, :3]
+    assert np.allclose(got, exp, rtol=2e-6, atol=1e-6)
+    assert ctx.eigen_features_batch(np.zeros((0, 6), np.float32)).shape == (0, 6)
+
+
+# ------------------------------------------------------------------------------ smoothing
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("shape,sigma", [((40, 48, 64), 1.0), ((4, 4, 4), 0.6), ((5, 17, 33), 2.4),
+                                         ((37, 16, 130), 4.8), ((19, 21, 23), 1.2)])
+def test_gaussian_bit_exact(ctx, oracle, arith, shape, sigma):
+    vol = synth.ct_like(shape, seed=2, n_blobs=6)
+    ctx.set_arith(arith)
+    try:
+        out = ctx.gaussian(vol, sigma)
+    finally:
+        ctx.set_arith(1)
+    ref = oracle.smoothing_recursive_gaussian(vol, sigma, arith=arith)
+    n, worst = mismatch_report(out, ref)
+    assert n == 0, "%d voxels differ (max %.3g)" % (n, worst)
+
+
+def test_gaussian_anisotropic_and_errors(ctx, oracle):
+    import ife_b200
+    vol = synth.ct_like((20, 24, 28), seed=5, n_blobs=4)
+    sp = (0.7, 0.7, 2.5)
+    assert bits_equal(ctx.gaussian(vol, 2.0, spacing=sp),
+                      oracle.smoothing_recursive_gaussian(vol, 2.0, spacing=sp, arith=1))
+    with pytest.raises(ife_b200.IfeError) as e:
+        ctx.gaussian(vol[:3], 1.0)          # ITK throws for < 4 samples per line
+    assert e.value.code == -2
+    with pytest.raises(ife_b200.IfeError) as e:
+        ctx.gaussian(vol, 0.0)
+    assert e.value.code == -1
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_normalized_gaussian_bit_exact(ctx, oracle, arith):
+    shape = (36, 40, 44)
+    img = synth.ct_like(shape, seed=7, n_blobs=8)
+    m8 = synth.clamp01(synth.lung_mask(shape))
+    ctx.set_arith(arith)
+    try:
+        out_u8 = ctx.normalized_gaussian(img, m8, 1.2)
+        cert = np.random.default_rng(0).uniform(0, 1, shape).astype(np.float32)
+        cert[m8 == 0] = 0
+        out_f = ctx.normalized_gaussian(img, cert, 2.4)
+        out_fm = ctx.normalized_gaussian(img, cert, 2.4, mask_output=True)
+    finally:
+        ctx.set_arith(1)
+    ref_u8 = oracle.normalized_gaussian(img, m8.astype(np.float32), 1.2, arith=arith)
+    ref_f = oracle.normalized_gaussian(img, cert, 2.4, arith=arith)
+    assert mismatch_report(out_u8, ref_u8)[0] == 0
+    assert mismatch_report(out_f, ref_f)[0] == 0
+    assert mismatch_report(out_fm, np.where(cert != 0, ref_f, np.float32(0)))[0] == 0
+
+
+def test_normalized_gaussian_zero_divisor_rule(ctx, oracle):
+    # certainty identically zero -> G(c) == 0 -> itk::DivideImageFilter yields float max
+    img = synth.ct_like((8, 8, 8), seed=1, n_blobs=2)
+    zero = np.zeros((8, 8, 8), np.uint8)
+    out = ctx.normalized_gaussian(img, zero, 1.0)
+    assert np.all(out == np.finfo(np.float32).max)
+    assert bits_equal(out, oracle.normalized_gaussian(img, zero.astype(np.float32), 1.0, arith=1))
+
+
+# ------------------------------------------------------------------------------ stencils
+def test_gradient_magnitude_bit_exact(ctx, oracle):
+    shape = (21, 33, 47)
+    img = synth.ct_like(shape, seed=8, n_blobs=5)
+    assert bits_equal(ctx.gradient_magnitude(img), oracle.gradient_magnitude(img))
+    m = synth.lung_mask(shape).astype(np.float32)      # the tool reads the mask as float
+    assert bits_equal(ctx.gradient_magnitude(img, m), oracle.fd_gradient_features(img, m))
+    sp = (0.8, 1.25, 3.0)
+    assert bits_equal(ctx.gradient_magnitude(img, spacing=sp), oracle.gradient_magnitude(img, spacing=sp))
+
+
+def test_fd_hessian_features_tool_semantics(ctx, oracle):
+    import ife_b200
+    shape = (30, 34, 38)
+    img = synth.ct_like(shape, seed=9, n_blobs=6)
+    mask = synth.lung_mask(shape)          # labels {0,1,2}: the tool tests mask == 0
+    out = ctx.hessian_eigen_features(img, mask)
+    ref = oracle.fd_hessian_features(img, mask)
+    assert np.all(out[:, mask == 0] == 0)
+    assert_eigen_parity(np.moveaxis(out, 0, -1), np.moveaxis(ref, 0, -1), "fdhf")
+    out = ctx.hessian_eigen_features(img, None, flags=ife_b200.FDHF_TOOL_DY_BUG)
+    ref = oracle.fd_hessian_features(img, None, fdhf_tool_bug=True)
+    assert_eigen_parity(np.moveaxis(out, 0, -1), np.moveaxis(ref, 0, -1), "fdhf dy-bug")
+    sp = (0.6, 0.6, 1.5)
+    out = ctx.hessian_eigen_features(img, mask, spacing=sp)
+    ref = oracle.fd_hessian_features(img, mask, spacing=sp)
+    assert_eigen_parity(np.moveaxis(out, 0, -1), np.moveaxis(ref, 0, -1), "fdhf anisotropic")
+    # a constant image has an exactly zero Hessian: diagonal branch, all features 0
+    flat = np.full(shape, -1000.0, np.float32)
+    assert np.all(ctx.hessian_eigen_features(flat) == 0)
+
+
+def test_config0_128cube_sigma1(ctx, oracle):
+    """BASELINE.json configs[0]: FiniteDifference_HessianFeatures on a synthetic 128^3 float
+    volume, single sigma = 1.0 (smooth with the library Gaussian, then the tool)."""
+    shape = (128, 128, 128)
+    img = synth.ct_like(shape, seed=1)
+    out = ctx.hessian_eigen_features(img, None, sigma=1.0)
+    ref = oracle.fd_hessian_features(img, None, sigma=1.0, arith=1)
+    assert_eigen_parity(np.moveaxis(out, 0, -1), np.moveaxis(ref, 0, -1), "config 0")
+    n, worst = mismatch_report(out, ref)
+    print("config0: %d of %d output values differ from the oracle (max abs %.3g)" % (n, out.size, worst))
+    e = out[:3].reshape(3, -1)
+    tol = 1e-5 * np.abs(e).max(0)
+    assert np.all(np.abs(e[0]) >= np.abs(e[1]) - tol) and np.all(np.abs(e[1]) >= np.abs(e[2]) - tol)
+
+
+# ------------------------------------------------------------------------------ full feature stack
+@pytest.mark.parametrize("arith", [0, 1])
+def test_emphysema_features_multiscale(ctx, oracle, arith):
+    shape = (48, 56, 72)
+    sigmas = [0.6, 1.2, 2.4, 4.8]
+    img = synth.ct_like(shape, seed=10, n_blobs=12)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    ctx.set_arith(arith)
+    try:
+        out = ctx.emphysema_features(img, mask, sigmas)
+    finally:
+        ctx.set_arith(1)
+    assert out.shape == (4, 8) + shape
+    for s, sigma in enumerate(sigmas):
+        ref = oracle.emphysema_features(img, mask, sigma, arith=arith)
+        assert np.all(out[s][:, mask == 0] == 0)
+        assert mismatch_report(out[s, 0], ref[0])[0] == 0, "blur sigma=%g" % sigma
+        assert mismatch_report(out[s, 1], ref[1])[0] == 0, "gradient magnitude sigma=%g" % sigma
+        assert_eigen_parity(np.moveaxis(out[s, 2:], 0, -1), np.moveaxis(ref[2:], 0, -1),
+                            "eigen features sigma=%g" % sigma)
+
+
+def test_emphysema_features_ragged_and_all_ones_mask(ctx, oracle):
+    shape = (7, 13, 35)
+    img = synth.ct_like(shape, seed=12, n_blobs=3)
+    ones = np.ones(shape, np.uint8)
+    out = ctx.emphysema_features(img, ones, [1.0])[0]
+    ref = oracle.emphysema_features(img, ones, 1.0, arith=1)
+    assert mismatch_report(out[:2], ref[:2])[0] == 0
+    assert_eigen_parity(np.moveaxis(out[2:], 0, -1), np.moveaxis(ref[2:], 0, -1), "ragged")
+    none = np.zeros(shape, np.uint8)
+    assert np.all(ctx.emphysema_features(img, none, [1.0]) == 0)
+
+
+# ------------------------------------------------------------------------------ histograms
+def test_histogram_flat_array(ctx, oracle):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hist_ref.npz"))
+    assert np.array_equal(ctx.histogram(g["values"], g["edges"]), g["counts"])
+    # test/DenseHistogramTest.cxx:10-31
+    vals = [-1, 0, 0.5, 1, 1.5, 2.1, 2.6, 2.9, 3.2, 3.5, 4.2, 4.6, 5, 6, 7, 8, 9, 10]
+    assert ctx.histogram(vals, [1, 2.5, 3.0, 4.7, 6.2, 8.3]).tolist() == [4, 2, 2, 4, 2, 2, 2]
+    assert ctx.histogram(np.zeros(0, np.float32), [0.0, 1.0]).tolist() == [0, 0, 0]
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(3_000_001).astype(np.float32)
+    e = np.sort(rng.standard_normal(40)).astype(np.float32)
+    assert np.array_equal(ctx.histogram(v, e), oracle.hist_f32(e, v)[0])
+    # heavy contention: every value in one bin
+    assert ctx.histogram(np.full(1_000_000, 0.25, np.float32), e).sum() == 1_000_000
+
+
+def _edges_for(oracle, img, mask, sigmas, n_edges=40):
+    rows = []
+    for sigma in sigmas:
+        f = oracle.emphysema_features(img, mask, sigma, arith=1)
+        for k in range(8):
+            rows.append(synth.equalized_edges(f[k][mask != 0], n_edges))
+    return np.stack(rows)
+
+
+def test_emphysema_histograms_whole_mask_and_rois(ctx, oracle):
+    shape = (40, 48, 56)
+    sigmas = [0.6, 2.4]
+    img = synth.ct_like(shape, seed=13, n_blobs=10)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    edges = _edges_for(oracle, img, mask, sigmas)
+    feats = np.concatenate([oracle.emphysema_features(img, mask, s, arith=1) for s in sigmas])
+    ref = oracle.features_histograms(feats, mask, edges)
+    got = ctx.emphysema_histograms(img, mask, sigmas, edges)
+    assert got.shape == ref.shape == (1, 16, 41)
+    assert np.all(got.sum(2) == mask.sum())          # every in-mask voxel lands in exactly one bin
+    diff = np.abs(got.astype(np.int64) - ref.astype(np.int64)).sum()
+    # eigen features may differ in the last bit for <= MISMATCH_FRAC of voxels; such a voxel
+    # changes bin only if it sits on an edge
+    assert diff <= 2 * max(1, int(MISMATCH_FRAC * mask.sum() * 12)), diff
+    assert np.array_equal(got[0, [0, 1, 8, 9]], ref[0, [0, 1, 8, 9]])   # blur/gradient rows exact
+    rois = synth.random_rois(mask, 6, (11, 9, 7), seed=3)
+    ref = oracle.features_histograms(feats, mask, edges, rois)
+    got = ctx.emphysema_histograms(img, mask, sigmas, edges, rois)
+    assert got.shape == ref.shape == (6, 16, 41)
+    assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).sum() <= 2
+
+
+def test_bad_arguments_are_rejected(ctx):
+    import ctypes
+    import ife_b200
+    L = ctx.L
+    d = (ctypes.c_int * 3)(8, 8, 8)
+    sp = (ctypes.c_double * 3)(1, 1, 1)
+    buf = np.zeros((8, 8, 8), np.float32)
+    p = buf.ctypes.data_as(ctypes.c_void_p)
+    assert L.ife_cuda_gaussian(ctx.h, None, p, d, sp, 1.0, 0) == -1
+    assert L.ife_cuda_gaussian(None, p, p, d, sp, 1.0, 0) == -1
+    bad = (ctypes.c_int * 3)(8, 0, 8)
+    assert L.ife_cuda_gaussian(ctx.h, p, p, bad, sp, 1.0, 0) == -1
+    assert b"dims" in L.ife_cuda_last_error(ctx.h)
+    with pytest.raises(ife_b200.IfeError):
+        ctx.emphysema_histograms(buf, np.ones((8, 8, 8), np.uint8), [1.0], np.zeros((8, 4), np.float32),
+                                 rois=[[0, 0, 0, 9, 1, 1]])
+
+
+# ------------------------------------------------------------------------------ full size
+def test_full_size_invariants_512x512x400(ctx):
+    """BASELINE.json configs[1] size; checked through size-independent properties."""
+    shape = (400, 512, 512)
+    rng = np.random.default_rng(2)
+    coarse = rng.standard_normal((26, 33, 33)).astype(np.float32)
+    import torch
+    img = torch.nn.functional.interpolate(torch.from_numpy(coarse)[None, None], size=shape,
+                                          mode="trilinear", align_corners=True)[0, 0].numpy()
+    img = np.ascontiguousarray(img * 300 - 800 + rng.standard_normal(shape).astype(np.float32) * 20)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    out = ctx.emphysema_features(img, mask, [1.2])[0]
+    inside = mask != 0
+    assert np.all(out[:, ~inside] == 0)
+    e = out[2:5][:, inside]
+    assert np.isfinite(out).all()
+    tol = 1e-5 * np.abs(e).max(0)
+    assert np.all(np.abs(e[0]) >= np.abs(e[1]) - tol) and np.all(np.abs(e[1]) >= np.abs(e[2]) - tol)
+    assert np.array_equal(out[5][inside], (e[0] + e[1]) + e[2])                 # LoG
+    assert np.array_equal(out[6][inside], (e[0] * e[1]) * e[2])                 # curvature
+    assert np.array_equal(out[7][inside], np.sqrt((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]))
+    # trace of the Hessian == 7-point Laplacian of the blur, up to float rounding
+    b = out[0]
+    z, y, x = 200, 256, 150
+    assert inside[z, y, x]
+    lap = (b[z, y, x - 1] + b[z, y, x + 1] + b[z, y - 1, x] + b[z, y + 1, x] + b[z - 1, y, x] +
+           b[z + 1, y, x] - 6.0 * b[z, y, x])
+    if inside[z - 1:z + 2, y - 1:y + 2, x - 1:x + 2].all():
+        assert abs(out[5][z, y, x] - lap) <= 1e-3 * max(1.0, abs(lap))
+    # histograms of the same run: row sums == number of in-mask voxels
+    edges = np.stack([synth.equalized_edges(out[k][inside][::97], 40) for k in range(8)])
+    counts = ctx.emphysema_histograms(img, mask, [1.2], edges)
+    assert np.all(counts.sum(2) == inside.sum())
+    for k in (0, 1, 2, 7):
+        ref = np.bincount(np.searchsorted(edges[k], out[k][inside], side="left"), minlength=41)
+        assert np.array_equal(counts[0, k], ref)
