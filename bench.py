@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: Gvoxel/s, multi-scale Hessian eigen
+features, 512^2 x 400 CT; % HBM peak).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--workload extract|hist|slab] [--mask ones|lung] [--arith fma|plain]
+
+One "step" = one pass of the hot path over one synthetic scan: ImageToEmphysemaFeaturesFilter
+semantics (masked normalized convolution -> gradient magnitude -> fused Hessian/eigen
+features -> mask) at sigma in {0.6, 1.2, 2.4, 4.8}, eight float feature volumes written per
+scale (tools/ExtractFeatures.cxx semantics, BASELINE.json configs[1]).  Units = voxel-scales
+(nx*ny*nz*|sigma|).  N > 1: one process per GPU (torchrun), one scan per GPU, no data-path
+collective (weak scaling); `--workload slab` instead cuts ONE volume into z-slabs with NCCL
+halo exchange (configs[3]).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max
+over ranks); `e2e` goes through the C ABI with pinned HOST buffers, H2D and D2H inside the
+timed region; `roofline` is the dominant kernel's algorithmic bytes / its measured launch
+time against MEASURED_PEAKS.json; `cpu_baseline` is the CPU oracle timed on this box's
+host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "image-feature-extraction_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SIGMAS = [0.6, 1.2, 2.4, 4.8]
+DIMS = (512, 512, 400)               # nx, ny, nz
+METRIC = "Gvoxel/s multi-scale Hessian eigen features, 512^2x400 CT"
+# algorithmic bytes per voxel-scale per kernel (pipeline P2 = 78 B):
+#   z pass r(4 img + 1 mask) w8 | x pass r8 w8 | y pass r8 w4 (divide fused) | fused r(4+1) w32
+ALGO_BYTES = {"gauss_pass_z": 13, "gauss_pass_x": 16, "gauss_pass_y": 12, "features_fused": 37}
+ALGO_BYTES_HIST = {"gauss_pass_z": 13, "gauss_pass_x": 16, "gauss_pass_y": 12, "features_fused": 5}
+CPU_SAMPLE_NZ = 64                   # cpu_baseline sample: 512 x 512 x 64, all four scales
+REF_STEP_NZ = 16                     # --impl reference: planes per step
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def synth_scan_torch(torch, device, seed, mask_kind):
+    """CT-like volume generated on the device (same recipe as tests/synth.py in spirit:
+    smooth structures + tube + plate + noise) and a lung-shaped or all-ones mask."""
+    nx, ny, nz = DIMS
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    coarse = torch.randn((1, 1, nz // 16 + 1, ny // 16 + 1, nx // 16 + 1), generator=g, device=device)
+    img = torch.nn.functional.interpolate(coarse, size=(nz, ny, nx), mode="trilinear",
+                                          align_corners=True)[0, 0]
+    img = img * 300.0 - 800.0
+    y = torch.arange(ny, device=device, dtype=torch.float32)[None, :, None]
+    x = torch.arange(nx, device=device, dtype=torch.float32)[None, None, :]
+    img += 500.0 * torch.exp(-((y - ny * 0.37) ** 2 + (x - nx * 0.61) ** 2) / 8.0)
+    img += 300.0 * torch.exp(-((y - ny * 0.7) ** 2) / 4.5)
+    img += 30.0 * torch.randn((nz, ny, nx), generator=g, device=device)
+    img = img.contiguous()
+    if mask_kind == "ones":
+        mask = torch.ones((nz, ny, nx), dtype=torch.uint8, device=device)
+    else:
+        import synth
+        mask = torch.from_numpy(synth.clamp01(synth.lung_mask((nz, ny, nx)))).to(device)
+    return img, mask
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; ITK itself cannot be built in
+    this image) on this box's host cores, same metric/config, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as O
+    import synth
+    O.build()
+    cores = os.cpu_count() or 1
+    nx, ny, _ = DIMS
+    shape = (REF_STEP_NZ, ny, nx)
+    img = synth.ct_like(shape, seed=2, n_blobs=64)
+    mask = np.ones(shape, np.uint8) if args.mask == "ones" else synth.clamp01(synth.lung_mask((400, ny, nx)))[192:192 + REF_STEP_NZ]
+    units = img.size * len(SIGMAS)
+
+    def step():
+        for s in SIGMAS:
+            O.emphysema_features_reference_arm(img, mask, s, arith=O.ARITH_PLAIN, threads=cores)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = units / dt / 1e9
+    sample = "%dx%dx%d sub-volume x %d scales per step" % (nx, ny, REF_STEP_NZ, len(SIGMAS))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 recursion / f32 stencil+solver",
+        "data": "synthetic",
+        "config": {"workload": "ExtractFeatures multi-scale eigen features 512x512x400 sigma{0.6,1.2,2.4,4.8} "
+                               "(reference arm: bounded sample %s)" % sample, "mask": args.mask},
+        "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores,
+                         "kind": "port" if not O.ref_available() else "port+reference-functor",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(torch, img_dev, mask_dev):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    img = img_dev[:CPU_SAMPLE_NZ].cpu().numpy()
+    mask = mask_dev[:CPU_SAMPLE_NZ].cpu().numpy()
+    t0 = time.perf_counter()
+    for s in SIGMAS:
+        O.emphysema_features_reference_arm(img, mask, s, arith=O.ARITH_PLAIN, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": img.size * len(SIGMAS) / dt / 1e9, "unit": "Gvoxel/s", "cores": cores,
+            "kind": "port+reference-functor" if O.ref_available() else "port",
+            "sample": "%dx%dx%d sub-volume of the same scan, all %d scales, %.1f s of CPU work "
+                      "(ITK stages restated; per-voxel functor = reference header)" %
+                      (DIMS[0], DIMS[1], CPU_SAMPLE_NZ, len(SIGMAS), dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="extract", choices=["extract", "hist", "slab"])
+    ap.add_argument("--mask", default="ones", choices=["ones", "lung"])
+    ap.add_argument("--arith", default="fma", choices=["fma", "plain"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import ife_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    nx, ny, nz = DIMS
+    n = nx * ny * nz
+    ctx = ife_b200.Context(local_rank, arith=ife_b200.ARITH_FMA if args.arith == "fma" else ife_b200.ARITH_PLAIN)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    img, mask = synth_scan_torch(torch, dev, 100 + rank, args.mask)
+    hist = args.workload == "hist"
+    edges = None
+    if hist:
+        edges = np.tile(np.linspace(-1.0, 1.0, 40, dtype=np.float32), (len(SIGMAS) * 8, 1))
+        edges[0::8] = np.linspace(-1100, 0, 40)       # blur rows
+        edges[1::8] = np.linspace(0, 200, 40)         # gradient magnitude rows
+        counts = torch.zeros((1, len(SIGMAS) * 8, 41), dtype=torch.int32, device=dev)
+        out = None
+    else:
+        out = torch.empty((len(SIGMAS), 8, nz, ny, nx), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        if hist:
+            ctx.emphysema_histograms_dev(img.data_ptr(), mask.data_ptr(), counts.data_ptr(), DIMS, SIGMAS, edges)
+        else:
+            ctx.emphysema_features_dev(img.data_ptr(), mask.data_ptr(), out.data_ptr(), DIMS, SIGMAS)
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ctx.profile_enable(True)
+        l0 = ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        launches = ctx.launch_count() - l0
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    units = n * len(SIGMAS)
+    ms_per_step = ms / args.steps
+    value = world * units / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (rank 0's launches)
+    peak, peak_src = measured_peaks()
+    algo = ALGO_BYTES_HIST if hist else ALGO_BYTES
+    kinds = {k: v for k, v in prof.items() if v[1] > 0 and k in algo}
+    dom = max(kinds, key=lambda k: kinds[k][0])
+    per_kernel = {}
+    for k, (tms, cnt) in kinds.items():
+        gbs = algo[k] * n / (tms / cnt * 1e-3) / 1e9
+        per_kernel[k] = {"ms_per_launch": tms / cnt, "launches": cnt, "algo_bytes_per_voxel": algo[k],
+                         "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": tms / ms}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from an ncu --set full capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": per_kernel[dom]["achieved_gbs"] / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernels": per_kernel,
+                "pipeline": {"algo_bytes_per_voxel_scale": sum(algo.values()),
+                             "achieved_gbs": sum(algo.values()) * units / (ms_per_step * 1e-3) / 1e9,
+                             "frac": sum(algo.values()) * units / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        h_img = torch.empty((nz, ny, nx), dtype=torch.float32, pin_memory=True).copy_(img)
+        h_mask = torch.empty((nz, ny, nx), dtype=torch.uint8, pin_memory=True).copy_(mask)
+        L = ctx.L
+        import ctypes as C
+        dims_c, sp_c = (C.c_int * 3)(*DIMS), (C.c_double * 3)(1, 1, 1)
+        sig_c = (C.c_double * len(SIGMAS))(*SIGMAS)
+        if hist:
+            h_counts = np.zeros((1, len(SIGMAS) * 8, 41), np.uint32)
+            d2h = h_counts.nbytes
+            del counts
+
+            def e2e_step():
+                rc = L.ife_cuda_emphysema_histograms(ctx.h, C.c_void_p(h_img.data_ptr()), C.c_void_p(h_mask.data_ptr()),
+                                                     dims_c, sp_c, sig_c, len(SIGMAS), edges.ctypes.data_as(C.c_void_p), 40,
+                                                     None, 0, h_counts.ctypes.data_as(C.c_void_p), ife_b200.MEM_HOST)
+                ctx._check(rc)
+        else:
+            del out
+            torch.cuda.empty_cache()
+            h_out = torch.empty((len(SIGMAS), 8, nz, ny, nx), dtype=torch.float32, pin_memory=True)
+            d2h = h_out.numel() * 4
+
+            def e2e_step():
+                rc = L.ife_cuda_emphysema_features(ctx.h, C.c_void_p(h_img.data_ptr()), C.c_void_p(h_mask.data_ptr()),
+                                                   C.c_void_p(h_out.data_ptr()), dims_c, sp_c, sig_c, len(SIGMAS),
+                                                   ife_b200.MEM_HOST)
+                ctx._check(rc)
+        e_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()          # synchronous: returns when the outputs are in host memory
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        if dist:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * units / dt / 1e9, "unit": "Gvoxel/s", "ms_per_step": dt * 1e3, "steps": e_steps,
+               "h2d_bytes_per_step": int(h_img.numel() * 4 + h_mask.numel()), "d2h_bytes_per_step": int(d2h),
+               "api": "ife_cuda_emphysema_%s(..., IFE_MEM_HOST) with pinned host buffers" % ("histograms" if hist else "features")}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(torch, img, mask)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 recursion / f32 stencil+solver", "data": "synthetic",
+            "config": {"workload": ("ExtractFeatures multi-scale eigen features (8 masked feature volumes per scale)"
+                                    if not hist else "MakeBag-style: same features binned into DenseHistograms, no feature volumes written")
+                                   + " on one 512x512x400 float CT-like scan per GPU, sigma{0.6,1.2,2.4,4.8}",
+                       "mask": args.mask, "arith": args.arith, "parallelism": "1 scan per GPU, no data-path collective",
+                       "l2": "inputs (525 MB/scan) and every intermediate are larger than the 126 MB L2; no flush needed"},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
+        }))
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

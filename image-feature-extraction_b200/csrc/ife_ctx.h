@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -35,6 +36,17 @@ struct Workspace {
 
 int fail(ife_cuda_ctx* ctx, int code, const char* fmt, ...);
 
+// kernel kinds for ife_cuda_profile_read
+enum { K_PASS_Z = 0, K_PASS_X = 1, K_PASS_Y = 2, K_FEATURES = 3, K_OTHER = 4, K_NUM = 5 };
+
+// RAII: records a CUDA event before and after a kernel launch when profiling is on
+struct ProfScope {
+  ife_cuda_ctx* ctx;
+  cudaEvent_t end = nullptr;
+  ProfScope(ife_cuda_ctx* c, int kind);
+  ~ProfScope();
+};
+
 }  // namespace ife
 
 struct ife_cuda_ctx {
@@ -49,6 +61,11 @@ struct ife_cuda_ctx {
   uint64_t launches = 0;
   std::string error;
   ife::Workspace ws;
+  // optional per-kernel timing (ife_cuda_profile_*): event pairs around every launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // 2 per launch: begin, end
+  std::vector<int> prof_kinds;
+  size_t prof_used = 0;                  // events handed out since the last read
   // NCCL (resolved lazily with dlopen; see slab.cu)
   void* nccl_comm = nullptr;
   int n_ranks = 1;

@@ -44,6 +44,24 @@ int fail(ife_cuda_ctx* ctx, int code, const char* fmt, ...) {
     if (rc_ != IFE_OK) return rc_; \
   } while (0)
 
+ProfScope::ProfScope(ife_cuda_ctx* c, int kind) : ctx(c) {
+  if (!c->profiling) return;
+  if (c->prof_used + 2 > c->prof_events.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      c->prof_events.push_back(e);
+    }
+  }
+  cudaEventRecord(c->prof_events[c->prof_used], c->stream());
+  end = c->prof_events[c->prof_used + 1];
+  c->prof_used += 2;
+  c->prof_kinds.push_back(kind);
+}
+ProfScope::~ProfScope() {
+  if (end) cudaEventRecord(end, ctx->stream());
+}
+
 int DeviceBuffer::reserve(ife_cuda_ctx* ctx, size_t want) {
   if (want <= bytes) return IFE_OK;
   if (ptr) {
@@ -150,6 +168,7 @@ size_t ckpt_bytes_volume(int nf, int nx, int ny, int nz) {
 template <int NF, int INMODE, bool DIVIDE>
 int launch_strided(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
   const unsigned grid = (unsigned)((A.n_lines + 127) / 128);
+  ProfScope prof(ctx, A.stride == (long long)A.na && A.sb == 0 ? K_PASS_Z : K_PASS_Y);
   if (ctx->arith == IFE_ARITH_FMA)
     gauss_pass_strided<NF, INMODE, DIVIDE, kChunk, true><<<grid, 128, 0, ctx->stream()>>>(C, A);
   else
@@ -163,6 +182,7 @@ template <int NF>
 int launch_x(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
   const long long lines_per_block = 32LL * kXWarps;
   const unsigned grid = (unsigned)((A.n_lines + lines_per_block - 1) / lines_per_block);
+  ProfScope prof(ctx, K_PASS_X);
   if (ctx->arith == IFE_ARITH_FMA)
     gauss_pass_x<NF, kChunk, true, kXWarps><<<grid, 32 * kXWarps, 0, ctx->stream()>>>(C, A);
   else
@@ -258,6 +278,7 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
   if (smem > 48 * 1024)
     return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d) for shared memory", A.hist.n_edges);
   cudaStream_t st = ctx->stream();
+  ProfScope prof(ctx, mode == 2 ? K_OTHER : K_FEATURES);
   if (mode == 0) {
     if (hist) features_kernel<0, true><<<grid, block, smem, st>>>(S, A);
     else features_kernel<0, false><<<grid, block, 0, st>>>(S, A);
@@ -334,6 +355,7 @@ void ife_cuda_destroy(ife_cuda_ctx* ctx) {
   ife_cuda_comm_destroy(ctx);
   ctx->ws.release_all();
   for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->prof_events) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -369,6 +391,31 @@ int ife_cuda_synchronize(ife_cuda_ctx* ctx) {
 }
 
 uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ife_cuda_profile_enable(ife_cuda_ctx* ctx, int on) {
+  if (!ctx) return IFE_E_INVALID;
+  ctx->profiling = on != 0;
+  ctx->prof_used = 0;
+  ctx->prof_kinds.clear();
+  return IFE_OK;
+}
+
+int ife_cuda_profile_read(ife_cuda_ctx* ctx, double ms[IFE_PROFILE_KINDS],
+                          uint64_t launches[IFE_PROFILE_KINDS]) {
+  if (!ctx || !ms || !launches) return IFE_E_INVALID;
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  for (int k = 0; k < IFE_PROFILE_KINDS; ++k) { ms[k] = 0.0; launches[k] = 0; }
+  for (size_t i = 0; i < ctx->prof_kinds.size(); ++i) {
+    float t = 0.f;
+    IFE_CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+    ms[ctx->prof_kinds[i]] += t;
+    launches[ctx->prof_kinds[i]]++;
+  }
+  ctx->prof_used = 0;
+  ctx->prof_kinds.clear();
+  return IFE_OK;
+}
 
 int ife_cuda_reserve(ife_cuda_ctx* ctx, const int dims[3], int n_outputs) {
   if (!ctx || !dims) return IFE_E_INVALID;

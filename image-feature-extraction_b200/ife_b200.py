@@ -60,6 +60,8 @@ def load_library():
     L.ife_cuda_reserve.argtypes = [vp, ip, i]
     L.ife_cuda_launch_count.argtypes = [vp]
     L.ife_cuda_launch_count.restype = C.c_uint64
+    L.ife_cuda_profile_enable.argtypes = [vp, i]
+    L.ife_cuda_profile_read.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
     L.ife_cuda_gaussian.argtypes = [vp, vp, vp, ip, dp, d, i]
     L.ife_cuda_normalized_gaussian.argtypes = [vp, vp, vp, vp, vp, ip, dp, d, i, i]
     L.ife_cuda_gradient_magnitude.argtypes = [vp, vp, vp, vp, vp, ip, dp, i]
@@ -167,6 +169,18 @@ class Context:
 
     def launch_count(self):
         return int(self.L.ife_cuda_launch_count(self.h))
+
+    PROFILE_KINDS = ["gauss_pass_z", "gauss_pass_x", "gauss_pass_y", "features_fused", "other"]
+
+    def profile_enable(self, on=True):
+        self._check(self.L.ife_cuda_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """-> {kind: (total_ms, launches)} since the last read (synchronises)."""
+        ms = (C.c_double * 5)()
+        n = (C.c_uint64 * 5)()
+        self._check(self.L.ife_cuda_profile_read(self.h, ms, n))
+        return {k: (ms[j], int(n[j])) for j, k in enumerate(self.PROFILE_KINDS)}
 
     # ---- host-array conveniences (IFE_MEM_HOST); volumes are (nz, ny, nx) numpy arrays
     def gaussian(self, vol, sigma, spacing=None):

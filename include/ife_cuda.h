@@ -88,6 +88,16 @@ int ife_cuda_reserve(ife_cuda_ctx* ctx, const int dims[3], int n_outputs);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx);
 
+/* Optional per-kernel timing for benchmarks: while enabled, every kernel launch of the
+ * context is bracketed by CUDA events on the launching stream.  ife_cuda_profile_read
+ * synchronises, returns the summed device time (ms) and launch count per kernel kind since
+ * the last read, and resets.  Kinds: 0 = Gaussian z pass, 1 = x pass, 2 = y pass,
+ * 3 = fused Hessian/eigen/feature(/histogram) kernel, 4 = other. */
+#define IFE_PROFILE_KINDS 5
+int ife_cuda_profile_enable(ife_cuda_ctx* ctx, int on);
+int ife_cuda_profile_read(ife_cuda_ctx* ctx, double ms[IFE_PROFILE_KINDS],
+                          uint64_t launches[IFE_PROFILE_KINDS]);
+
 /* ---- per-stage entry points ------------------------------------------------------ */
 
 /* itk::SmoothingRecursiveGaussianImageFilter<float image> as the reference uses it

@@ -328,3 +328,25 @@ class Ref:
 
 def ref_available():
     return os.path.exists(os.path.join(_HERE, "_ref", "libife_ref.so"))
+
+
+def emphysema_features_reference_arm(img, mask, sigma, spacing=None, arith=ARITH_PLAIN, threads=None):
+    """The CPU baseline composition: restated ITK stages wired as
+    ImageToEmphysemaFeaturesFilter.hxx:11-55,94-121, with the per-voxel functor taken from
+    the reference's own header (oracle/_ref, incl. its per-voxel heap allocations) when
+    that library is present, else from the restatement.  -> (8, nz, ny, nx)"""
+    img = np.ascontiguousarray(img, np.float32)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    threads = threads or n_threads_default()
+    blur = normalized_gaussian(img, mask.astype(np.float32), sigma, spacing, arith, threads)
+    gm = gradient_magnitude(blur, spacing, threads)
+    hess = hessian6(blur, spacing, False, threads)
+    feat = (Ref().functor_volume(hess, None, threads) if ref_available()
+            else functor_volume(hess, None, threads))
+    out = np.empty((8,) + img.shape, np.float32)
+    inside = mask != 0
+    out[0] = np.where(inside, blur, np.float32(0))
+    out[1] = np.where(inside, gm, np.float32(0))
+    for k in range(6):
+        out[2 + k] = np.where(inside, feat[..., k], np.float32(0))
+    return out
