@@ -264,34 +264,46 @@ int reserve_smoothing(ife_cuda_ctx* ctx, int nf, int nx, int ny, int nzb) {
 // ---------------------------------------------------------------------------------------
 // Fused feature kernel launch
 // ---------------------------------------------------------------------------------------
-int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const FeatArgs& A) {
+template <int MODE, bool HIST>
+void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       const StencilCoef& S, const FeatArgs& A) {
+  if (unit) features_kernel<MODE, HIST, true><<<grid, block, smem, st>>>(S, A);
+  else features_kernel<MODE, HIST, false><<<grid, block, smem, st>>>(S, A);
+}
+
+int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const FeatArgs& A,
+                    bool unit_spacing) {
   const bool hist = A.hist.edges != nullptr;
   const int nfeat = mode == 0 ? 8 : (mode == 1 ? 6 : 1);
-  const size_t n_out = (size_t)A.nx * A.ny * (size_t)(A.zb1 - A.zb0);
-  if (n_out == 0) return IFE_OK;
-  const int block = 256;
-  const size_t want = (n_out + block - 1) / block;
-  const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * 32);
+  const int nzo = A.zb1 - A.zb0;
+  if (nzo <= 0 || A.nx <= 0 || A.ny <= 0) return IFE_OK;
+  const dim3 block(kTX, kTY, 1);
+  const dim3 grid((A.nx + kTX - 1) / kTX, (A.ny + kTY - 1) / kTY, (nzo + kTZ - 1) / kTZ);
+  if (grid.y > 65535 || grid.z > 65535) return fail(ctx, IFE_E_INVALID, "volume too large for the launch grid");
   const size_t smem =
       hist ? (size_t)nfeat * (A.hist.n_edges * sizeof(float) + (A.hist.n_edges + 1) * sizeof(uint32_t))
            : 0;
-  if (smem > 48 * 1024)
+  if (smem > 30 * 1024)
     return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d) for shared memory", A.hist.n_edges);
   cudaStream_t st = ctx->stream();
   ProfScope prof(ctx, mode == 2 ? K_OTHER : K_FEATURES);
   if (mode == 0) {
-    if (hist) features_kernel<0, true><<<grid, block, smem, st>>>(S, A);
-    else features_kernel<0, false><<<grid, block, 0, st>>>(S, A);
+    if (hist) launch_features_t<0, true>(unit_spacing, grid, block, smem, st, S, A);
+    else launch_features_t<0, false>(unit_spacing, grid, block, 0, st, S, A);
   } else if (mode == 1) {
-    if (hist) features_kernel<1, true><<<grid, block, smem, st>>>(S, A);
-    else features_kernel<1, false><<<grid, block, 0, st>>>(S, A);
+    if (hist) launch_features_t<1, true>(unit_spacing, grid, block, smem, st, S, A);
+    else launch_features_t<1, false>(unit_spacing, grid, block, 0, st, S, A);
   } else {
-    if (hist) features_kernel<2, true><<<grid, block, smem, st>>>(S, A);
-    else features_kernel<2, false><<<grid, block, 0, st>>>(S, A);
+    if (hist) launch_features_t<2, true>(unit_spacing, grid, block, smem, st, S, A);
+    else launch_features_t<2, false>(unit_spacing, grid, block, 0, st, S, A);
   }
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
   return IFE_OK;
+}
+
+inline bool is_unit_spacing(const double spacing[3]) {
+  return spacing[0] == 1.0 && spacing[1] == 1.0 && spacing[2] == 1.0;
 }
 
 int check_dims(ife_cuda_ctx* ctx, const int dims[3], const double spacing[3]) {
@@ -514,7 +526,7 @@ int ife_cuda_gradient_magnitude(ife_cuda_ctx* ctx, const float* in, const float*
   std::memset(&A, 0, sizeof(A));
   A.vol = d_in; A.mask_u8 = d_mu; A.mask_f32 = d_mf; A.out[0] = d_out;
   A.nx = dims[0]; A.ny = dims[1]; A.nzb = dims[2]; A.zb0 = 0; A.zb1 = dims[2];
-  IFE_TRY(launch_features(ctx, 2, make_stencil_coef(spacing), A));
+  IFE_TRY(launch_features(ctx, 2, make_stencil_coef(spacing), A, is_unit_spacing(spacing)));
   if (mem == IFE_MEM_HOST) {
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost,
                                       ctx->stream()));
@@ -554,7 +566,7 @@ int ife_cuda_hessian_eigen_features(ife_cuda_ctx* ctx, const float* image, const
   for (int k = 0; k < 6; ++k) A.out[k] = d_out + (size_t)k * n;
   A.nx = dims[0]; A.ny = dims[1]; A.nzb = dims[2]; A.zb0 = 0; A.zb1 = dims[2];
   A.dy_bug = (flags & IFE_FDHF_TOOL_DY_BUG) ? 1 : 0;
-  IFE_TRY(launch_features(ctx, 1, make_stencil_coef(spacing), A));
+  IFE_TRY(launch_features(ctx, 1, make_stencil_coef(spacing), A, is_unit_spacing(spacing)));
   if (mem == IFE_MEM_HOST) {
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out6, d_out, 6 * n * sizeof(float), cudaMemcpyDeviceToHost,
                                       ctx->stream()));
@@ -597,7 +609,7 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
     A.vol = blur; A.mask_u8 = d_mask;
     for (int k = 0; k < 8; ++k) A.out[k] = d_out + (size_t)k * n;
     A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
-    IFE_TRY(launch_features(ctx, 0, S, A));
+    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
     if (mem == IFE_MEM_HOST) {
       IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[s & 1], ctx->stream()));
       IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[s & 1], 0));
@@ -672,7 +684,7 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
     A.hist.counts = d_counts + (size_t)s * 8 * nb;
     A.hist.rois = d_rois; A.hist.n_roi = n_roi; A.hist.n_edges = n_edges;
     A.hist.stride_roi = (long long)rows * nb;
-    IFE_TRY(launch_features(ctx, 0, S, A));
+    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
   }
   if (mem == IFE_MEM_HOST) {
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, n_counts * sizeof(uint32_t),

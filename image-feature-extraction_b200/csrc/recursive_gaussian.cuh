@@ -114,16 +114,19 @@ __device__ __forceinline__ size_t ckpt_index(int chunk, int f, int k, size_t n_l
 
 // ---------------------------------------------------------------------------------------
 // Phase A over one chunk already in registers: advance the causal recurrence.
+// GENERIC = false is the hot path: a full chunk (len == L) strictly inside the line, no
+// predicates and constant feedback coefficients, so the fully unrolled body is nothing but
+// the recurrence.  GENERIC = true handles the first chunk (boundary coefficients), the
+// last chunk(s) and partial chunks.
 // ---------------------------------------------------------------------------------------
-template <int NF, int L, bool FMA>
+template <int NF, int L, bool FMA, bool GENERIC>
 __device__ __forceinline__ void forward_chunk(const GaussCoef& C, const float (&xs)[NF][L], int i0,
                                               int len, Rec (&cs)[NF]) {
   Fb fb = fb_select(C.D, C.BN, 4);
-  const bool bnd = i0 < 4;
 #pragma unroll
   for (int j = 0; j < L; ++j) {
-    if (j < len) {
-      if (bnd) fb = fb_select(C.D, C.BN, i0 + j);
+    if (!GENERIC || j < len) {
+      if (GENERIC) fb = fb_select(C.D, C.BN, i0 + j);
 #pragma unroll
       for (int f = 0; f < NF; ++f) causal_step<FMA>(C, fb, cs[f], (double)xs[f][j]);
     }
@@ -135,17 +138,16 @@ __device__ __forceinline__ void forward_chunk(const GaussCoef& C, const float (&
 // anticausal recurrence backward from `as` (state at i0+len); result float(y+w) replaces
 // xs in place.
 // ---------------------------------------------------------------------------------------
-template <int NF, int L, bool FMA>
+template <int NF, int L, bool FMA, bool GENERIC>
 __device__ __forceinline__ void backward_chunk(const GaussCoef& C, float (&xs)[NF][L], int i0,
                                                int len, int n, Rec (&cs)[NF], Rec (&as)[NF]) {
   double yb[NF][L];
   {
     Fb fb = fb_select(C.D, C.BN, 4);
-    const bool bnd = i0 < 4;
 #pragma unroll
     for (int j = 0; j < L; ++j) {
-      if (j < len) {
-        if (bnd) fb = fb_select(C.D, C.BN, i0 + j);
+      if (!GENERIC || j < len) {
+        if (GENERIC) fb = fb_select(C.D, C.BN, i0 + j);
 #pragma unroll
         for (int f = 0; f < NF; ++f) yb[f][j] = causal_step<FMA>(C, fb, cs[f], (double)xs[f][j]);
       }
@@ -153,11 +155,10 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, float (&xs)[N
   }
   {
     Fb fb = fb_select(C.D, C.BM, 4);
-    const bool bnd = i0 + len + 3 > n - 1;  // some tap of this chunk reaches past the end
 #pragma unroll
     for (int j = L - 1; j >= 0; --j) {
-      if (j < len) {
-        if (bnd) fb = fb_select(C.D, C.BM, n - 1 - (i0 + j));
+      if (!GENERIC || j < len) {
+        if (GENERIC) fb = fb_select(C.D, C.BM, n - 1 - (i0 + j));
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const double w = anti_step<FMA>(C, fb, as[f], (double)xs[f][j]);
@@ -166,6 +167,12 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, float (&xs)[N
       }
     }
   }
+}
+
+// chunk [i0, i0+len) of a line of n samples can take the hot path
+template <int L>
+__device__ __forceinline__ bool chunk_is_interior(int i0, int len, int n) {
+  return len == L && i0 >= 4 && i0 + len + 3 <= n - 1;
 }
 
 // itk::DivideImageFilter functor: b != 0 ? a/b : NumericTraits<float>::max()
@@ -244,7 +251,8 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
         A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
       }
     }
-    forward_chunk<NF, L, FMA>(C, xs, i0, len, cs);
+    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, xs, i0, len, cs);
+    else forward_chunk<NF, L, FMA, true>(C, xs, i0, len, cs);
   }
 
   // ---- phase B: backward over chunks ----
@@ -296,7 +304,8 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
         cs[f].x3 = 0.0;
       }
     }
-    backward_chunk<NF, L, FMA>(C, xs, i0, len, n, cs, as);
+    if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, xs, i0, len, n, cs, as);
+    else backward_chunk<NF, L, FMA, true>(C, xs, i0, len, n, cs, as);
 #pragma unroll
     for (int j = 0; j < L; ++j) {
       if (j < len) {
@@ -405,7 +414,8 @@ gauss_pass_x(const __grid_constant__ GaussCoef C, const __grid_constant__ PassAr
         A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
       }
     }
-    forward_chunk<NF, L, FMA>(C, xs, i0, len, cs);
+    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, xs, i0, len, cs);
+    else forward_chunk<NF, L, FMA, true>(C, xs, i0, len, cs);
   }
 
   Rec as[NF];
@@ -445,7 +455,8 @@ gauss_pass_x(const __grid_constant__ GaussCoef C, const __grid_constant__ PassAr
         cs[f].x3 = 0.0;
       }
     }
-    backward_chunk<NF, L, FMA>(C, xs, i0, len, n, cs, as);
+    if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, xs, i0, len, n, cs, as);
+    else backward_chunk<NF, L, FMA, true>(C, xs, i0, len, n, cs, as);
     xtile_store<NF, L>(A, T, line0, i0, len, lane, xs);
   }
 }

@@ -237,7 +237,7 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
       A.hist.n_roi = 0;
       A.hist.stride_roi = (long long)rows * nb;
     }
-    IFE_TRY(launch_features(ctx, 0, S, A));
+    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
     if (out && mem == IFE_MEM_HOST)
       IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n_own, d_out, 8 * n_own * sizeof(float),
                                         cudaMemcpyDeviceToHost, st));
