@@ -59,6 +59,7 @@ struct ife_cuda_ctx {
   bool use_user_stream = false;
   cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
+  bool use_async = true;   // cp.async software-pipelined Gaussian passes (option "async_passes")
   std::string error;
   ife::Workspace ws;
   // optional per-kernel timing (ife_cuda_profile_*): event pairs around every launch

@@ -165,14 +165,35 @@ size_t ckpt_bytes_volume(int nf, int nx, int ny, int nz) {
   return std::max(a, std::max(b, c));
 }
 
+constexpr int kAsyncStages = 3;
+
+template <int NF, int INMODE, bool DIVIDE, bool FMA>
+int launch_strided_async(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
+  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, kChunk, FMA, kAsyncStages>;
+  const size_t smem = sizeof(AsyncStage<NF, INMODE, kChunk>) * kAsyncStages;
+  IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((A.n_lines + kAsyncThreads - 1) / kAsyncThreads);
+  kern<<<grid, kAsyncThreads, smem, ctx->stream()>>>(C, A);
+  return IFE_OK;
+}
+
 template <int NF, int INMODE, bool DIVIDE>
 int launch_strided(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
   const unsigned grid = (unsigned)((A.n_lines + 127) / 128);
   ProfScope prof(ctx, A.stride == (long long)A.na && A.sb == 0 ? K_PASS_Z : K_PASS_Y);
-  if (ctx->arith == IFE_ARITH_FMA)
+  // software-pipelined kernel unless the uint8 mask cannot be moved in aligned 4-byte pieces
+  bool async_ok = ctx->use_async;
+  if (INMODE == IN_IMG_U8)
+    async_ok = async_ok && A.sb == 0 && (reinterpret_cast<uintptr_t>(A.in1) % 4 == 0) &&
+               A.stride % 4 == 0 && A.n_lines % 4 == 0;
+  if (async_ok) {
+    if (ctx->arith == IFE_ARITH_FMA) IFE_TRY((launch_strided_async<NF, INMODE, DIVIDE, true>(ctx, C, A)));
+    else IFE_TRY((launch_strided_async<NF, INMODE, DIVIDE, false>(ctx, C, A)));
+  } else if (ctx->arith == IFE_ARITH_FMA) {
     gauss_pass_strided<NF, INMODE, DIVIDE, kChunk, true><<<grid, 128, 0, ctx->stream()>>>(C, A);
-  else
+  } else {
     gauss_pass_strided<NF, INMODE, DIVIDE, kChunk, false><<<grid, 128, 0, ctx->stream()>>>(C, A);
+  }
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
   return IFE_OK;
@@ -403,6 +424,12 @@ int ife_cuda_synchronize(ife_cuda_ctx* ctx) {
 }
 
 uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return IFE_E_INVALID;
+  if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
+  return fail(ctx, IFE_E_INVALID, "unknown option '%s'", name);
+}
 
 int ife_cuda_profile_enable(ife_cuda_ctx* ctx, int on) {
   if (!ctx) return IFE_E_INVALID;

@@ -113,34 +113,38 @@ __device__ __forceinline__ size_t ckpt_index(int chunk, int f, int k, size_t n_l
 }
 
 // ---------------------------------------------------------------------------------------
-// Phase A over one chunk already in registers: advance the causal recurrence.
+// Chunk processing, generic over where the samples come from (SRC: void(int j, double(&)[NF]))
+// and where the results go (SINK: void(int j, const float(&)[NF])).
+//
+// forward_chunk  : phase A, advance the causal recurrence over one chunk.
+// backward_chunk : phase B, replay causal from `cs` (state at i0) into registers, then run
+//                  the anticausal recurrence backward from `as` (state at i0+len) and emit
+//                  float(causal + anticausal).
 // GENERIC = false is the hot path: a full chunk (len == L) strictly inside the line, no
 // predicates and constant feedback coefficients, so the fully unrolled body is nothing but
 // the recurrence.  GENERIC = true handles the first chunk (boundary coefficients), the
 // last chunk(s) and partial chunks.
 // ---------------------------------------------------------------------------------------
-template <int NF, int L, bool FMA, bool GENERIC>
-__device__ __forceinline__ void forward_chunk(const GaussCoef& C, const float (&xs)[NF][L], int i0,
-                                              int len, Rec (&cs)[NF]) {
+template <int NF, int L, bool FMA, bool GENERIC, typename SRC>
+__device__ __forceinline__ void forward_chunk(const GaussCoef& C, const SRC& src, int i0, int len,
+                                              Rec (&cs)[NF]) {
   Fb fb = fb_select(C.D, C.BN, 4);
 #pragma unroll
   for (int j = 0; j < L; ++j) {
     if (!GENERIC || j < len) {
       if (GENERIC) fb = fb_select(C.D, C.BN, i0 + j);
+      double v[NF];
+      src(j, v);
 #pragma unroll
-      for (int f = 0; f < NF; ++f) causal_step<FMA>(C, fb, cs[f], (double)xs[f][j]);
+      for (int f = 0; f < NF; ++f) causal_step<FMA>(C, fb, cs[f], v[f]);
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// Phase B over one chunk in registers: replay causal from `cs` (state at i0), then run the
-// anticausal recurrence backward from `as` (state at i0+len); result float(y+w) replaces
-// xs in place.
-// ---------------------------------------------------------------------------------------
-template <int NF, int L, bool FMA, bool GENERIC>
-__device__ __forceinline__ void backward_chunk(const GaussCoef& C, float (&xs)[NF][L], int i0,
-                                               int len, int n, Rec (&cs)[NF], Rec (&as)[NF]) {
+template <int NF, int L, bool FMA, bool GENERIC, typename SRC, typename SINK>
+__device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& src, const SINK& sink,
+                                               int i0, int len, int n, Rec (&cs)[NF],
+                                               Rec (&as)[NF]) {
   double yb[NF][L];
   {
     Fb fb = fb_select(C.D, C.BN, 4);
@@ -148,8 +152,10 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, float (&xs)[N
     for (int j = 0; j < L; ++j) {
       if (!GENERIC || j < len) {
         if (GENERIC) fb = fb_select(C.D, C.BN, i0 + j);
+        double v[NF];
+        src(j, v);
 #pragma unroll
-        for (int f = 0; f < NF; ++f) yb[f][j] = causal_step<FMA>(C, fb, cs[f], (double)xs[f][j]);
+        for (int f = 0; f < NF; ++f) yb[f][j] = causal_step<FMA>(C, fb, cs[f], v[f]);
       }
     }
   }
@@ -159,11 +165,15 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, float (&xs)[N
     for (int j = L - 1; j >= 0; --j) {
       if (!GENERIC || j < len) {
         if (GENERIC) fb = fb_select(C.D, C.BM, n - 1 - (i0 + j));
+        double v[NF];
+        src(j, v);
+        float o[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-          const double w = anti_step<FMA>(C, fb, as[f], (double)xs[f][j]);
-          xs[f][j] = (float)__dadd_rn(yb[f][j], w);
+          const double w = anti_step<FMA>(C, fb, as[f], v[f]);
+          o[f] = (float)__dadd_rn(yb[f][j], w);
         }
+        sink(j, o);
       }
     }
   }
@@ -174,6 +184,24 @@ template <int L>
 __device__ __forceinline__ bool chunk_is_interior(int i0, int len, int n) {
   return len == L && i0 >= 4 && i0 + len + 3 <= n - 1;
 }
+
+// register-array source / sink (samples of the chunk already in registers)
+template <int NF, int L>
+struct RegSrc {
+  const float (&xs)[NF][L];
+  __device__ __forceinline__ void operator()(int j, double (&v)[NF]) const {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) v[f] = (double)xs[f][j];
+  }
+};
+template <int NF, int L>
+struct RegSink {
+  float (&xs)[NF][L];
+  __device__ __forceinline__ void operator()(int j, const float (&o)[NF]) const {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) xs[f][j] = o[f];
+  }
+};
 
 // itk::DivideImageFilter functor: b != 0 ? a/b : NumericTraits<float>::max()
 __device__ __forceinline__ float itk_divide(float a, float b) {
@@ -251,8 +279,11 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
         A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
       }
     }
-    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, xs, i0, len, cs);
-    else forward_chunk<NF, L, FMA, true>(C, xs, i0, len, cs);
+    {
+      const RegSrc<NF, L> src{xs};
+      if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, src, i0, len, cs);
+      else forward_chunk<NF, L, FMA, true>(C, src, i0, len, cs);
+    }
   }
 
   // ---- phase B: backward over chunks ----
@@ -304,8 +335,13 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
         cs[f].x3 = 0.0;
       }
     }
-    if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, xs, i0, len, n, cs, as);
-    else backward_chunk<NF, L, FMA, true>(C, xs, i0, len, n, cs, as);
+    {
+      // the sink overwrites xs[.][j] only after the anticausal step has consumed it
+      const RegSrc<NF, L> src{xs};
+      const RegSink<NF, L> sink{xs};
+      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
+      else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
+    }
 #pragma unroll
     for (int j = 0; j < L; ++j) {
       if (j < len) {
@@ -322,6 +358,217 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Strided lines, software-pipelined: the same sweep as gauss_pass_strided, but every chunk
+// (its L samples, the 3 samples of causal history before it and, in phase B, its
+// checkpoint) is brought into shared memory with cp.async STAGES-1 chunks ahead of its use.
+// Each thread copies exactly the bytes its own line needs into a slot only it reads, so no
+// block barrier is needed: cp.async.wait_group orders a thread's copies before its own
+// reads.  (The uint8 mask is the one exception: cp.async moves at least 4 bytes, so every
+// fourth lane copies the mask bytes of four adjacent lines and the warp synchronises.)
+// With 2 CTAs of 128 threads per SM and 3 stages, >100 KB per SM is in flight, which is what
+// hides HBM latency at the 8 resident warps the 200+ registers of the recurrence allow.
+// Requirements checked on the host (else the plain kernel runs): for IN_IMG_U8 the mask
+// pointer, the line stride and n_lines are multiples of 4.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kAsyncThreads = 128;
+
+template <int NF, int INMODE, int L>
+struct AsyncStage {
+  static constexpr int ROWS = L + 3;  // rows 0..2 = samples i0-3..i0-1, rows 3.. = the chunk
+  float f0[ROWS][kAsyncThreads];
+  // second field (float) or certainty (float / uint8, the latter packed in the first bytes)
+  float f1[NF == 2 ? ROWS : 1][kAsyncThreads];
+  double ck[NF * 4][kAsyncThreads];
+};
+
+template <int NF, int INMODE, int L>
+__device__ __forceinline__ void stage_sample(const AsyncStage<NF, INMODE, L>& S, int row, int t,
+                                             double (&v)[NF]) {
+  if (INMODE == IN_FIELDS) {
+    v[0] = (double)S.f0[row][t];
+    if (NF == 2) v[NF - 1] = (double)S.f1[NF == 2 ? row : 0][t];
+  } else {
+    const float img = S.f0[row][t];
+    float c;
+    if (INMODE == IN_IMG_U8)
+      c = (float)reinterpret_cast<const uint8_t*>(&S.f1[0][0])[row * kAsyncThreads + t];
+    else
+      c = S.f1[NF == 2 ? row : 0][t];
+    v[0] = (double)__fmul_rn(img, c);  // itk::MultiplyImageFilter
+    v[NF - 1] = (double)c;
+  }
+}
+
+// issue the copies of chunk kc (planes i0-3+row_first .. i0+len-1) into stage S
+template <int NF, int INMODE, int L>
+__device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, INMODE, L>& S, int t,
+                                            bool active, size_t base, size_t line, int kc,
+                                            int row_first, bool with_ckpt) {
+  constexpr int ROWS = L + 3;
+  const int i0 = kc * L;
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int plane = i0 - 3 + r;
+      if (r >= row_first && plane >= 0 && plane < A.n) {
+        const size_t idx = base + (size_t)plane * (size_t)A.stride;
+        cp_async4(&S.f0[r][t], A.in0 + idx);
+        if (NF == 2) {
+          if (INMODE == IN_IMG_U8) {
+            if ((t & 3) == 0)
+              cp_async4(reinterpret_cast<uint8_t*>(&S.f1[0][0]) + r * kAsyncThreads + t,
+                        reinterpret_cast<const uint8_t*>(A.in1) + idx);
+          } else {
+            cp_async4(&S.f1[NF == 2 ? r : 0][t], reinterpret_cast<const float*>(A.in1) + idx);
+          }
+        }
+      }
+    }
+    if (with_ckpt && kc >= 1) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          cp_async8(&S.ck[f * 4 + k][t], A.ckpt + ckpt_index<NF>(kc, f, k, A.n_lines, line));
+    }
+  }
+  cp_async_commit();
+}
+
+template <int NF, int INMODE, bool DIVIDE, int L, bool FMA, int STAGES>
+__global__ void __launch_bounds__(kAsyncThreads)
+gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_constant__ PassArgs A) {
+  using Stage = AsyncStage<NF, INMODE, L>;
+  extern __shared__ __align__(16) unsigned char async_smem[];
+  Stage* stages = reinterpret_cast<Stage*>(async_smem);
+  const int t = threadIdx.x;
+  const long long line_ll = (long long)blockIdx.x * kAsyncThreads + t;
+  const bool active = line_ll < A.n_lines;
+  const size_t line = (size_t)(active ? line_ll : A.n_lines - 1);
+  const size_t base = (size_t)(line % A.na) + (size_t)(line / A.na) * (size_t)A.sb;
+  const size_t st = (size_t)A.stride;
+  const int n = A.n;
+  const int n_chunks = (n + L - 1) / L;
+
+  Rec cs[NF];
+  Rec as[NF];
+
+  // ---- phase A: causal sweep, checkpoint at every chunk start ----
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < n_chunks) stage_issue<NF, INMODE, L>(A, stages[s], t, active, base, line, s, 3, false);
+    else cp_async_commit();
+  }
+  for (int k = 0; k < n_chunks; ++k) {
+    const int kn = k + STAGES - 1;
+    if (kn < n_chunks) stage_issue<NF, INMODE, L>(A, stages[kn % STAGES], t, active, base, line, kn, 3, false);
+    else cp_async_commit();
+    cp_async_wait<STAGES - 1>();
+    if (INMODE == IN_IMG_U8) __syncwarp();
+    const Stage& S = stages[k % STAGES];
+    const int i0 = k * L;
+    const int len = min(L, n - i0);
+    if (k == 0) {
+      double v[NF];
+      stage_sample<NF, INMODE, L>(S, 3, t, v);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) rec_fill(cs[f], v[f]);
+    } else if (active) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        A.ckpt[ckpt_index<NF>(k, f, 0, A.n_lines, line)] = cs[f].h0;
+        A.ckpt[ckpt_index<NF>(k, f, 1, A.n_lines, line)] = cs[f].h1;
+        A.ckpt[ckpt_index<NF>(k, f, 2, A.n_lines, line)] = cs[f].h2;
+        A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
+      }
+    }
+    auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L>(S, 3 + j, t, v); };
+    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, src, i0, len, cs);
+    else forward_chunk<NF, L, FMA, true>(C, src, i0, len, cs);
+    if (k == n_chunks - 1) {  // the line's last sample is the anticausal edge value
+      double v[NF];
+      stage_sample<NF, INMODE, L>(S, 3 + len - 1, t, v);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) rec_fill(as[f], v[f]);
+    }
+    if (INMODE == IN_IMG_U8) __syncwarp();  // mask bytes are shared by 4 lanes: all reads done
+  }
+  cp_async_wait<0>();
+  __threadfence_block();
+
+  // ---- phase B: backward over chunks, prefetching downwards ----
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    const int kc = n_chunks - 1 - s;
+    if (kc >= 0) stage_issue<NF, INMODE, L>(A, stages[s], t, active, base, line, kc, 0, true);
+    else cp_async_commit();
+  }
+  for (int q = 0; q < n_chunks; ++q) {
+    const int k = n_chunks - 1 - q;
+    const int qn = q + STAGES - 1;
+    if (qn < n_chunks)
+      stage_issue<NF, INMODE, L>(A, stages[qn % STAGES], t, active, base, line, n_chunks - 1 - qn, 0, true);
+    else cp_async_commit();
+    cp_async_wait<STAGES - 1>();
+    if (INMODE == IN_IMG_U8) __syncwarp();
+    const Stage& S = stages[q % STAGES];
+    const int i0 = k * L;
+    const int len = min(L, n - i0);
+    if (k == 0) {
+      double v[NF];
+      stage_sample<NF, INMODE, L>(S, 3, t, v);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) rec_fill(cs[f], v[f]);
+    } else {
+      double v1[NF], v2[NF], v3[NF];
+      stage_sample<NF, INMODE, L>(S, 2, t, v1);
+      stage_sample<NF, INMODE, L>(S, 1, t, v2);
+      stage_sample<NF, INMODE, L>(S, 0, t, v3);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        cs[f].h0 = S.ck[f * 4 + 0][t];
+        cs[f].h1 = S.ck[f * 4 + 1][t];
+        cs[f].h2 = S.ck[f * 4 + 2][t];
+        cs[f].h3 = S.ck[f * 4 + 3][t];
+        cs[f].x0 = v1[f];
+        cs[f].x1 = v2[f];
+        cs[f].x2 = v3[f];
+        cs[f].x3 = 0.0;
+      }
+    }
+    const size_t obase = base + (size_t)i0 * st;
+    auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L>(S, 3 + j, t, v); };
+    auto sink = [&](int j, const float (&o)[NF]) {
+      if (!active) return;
+      const size_t idx = obase + (size_t)j * st;
+      if (DIVIDE) {
+        float qv = itk_divide(o[0], o[NF - 1]);
+        if (A.mask_u8) qv = __ldg(A.mask_u8 + idx) != 0 ? qv : 0.0f;
+        if (A.mask_f32) qv = __ldg(A.mask_f32 + idx) != 0.0f ? qv : 0.0f;
+        A.out0[idx] = qv;
+      } else {
+        A.out0[idx] = o[0];
+        if (NF == 2) A.out1[idx] = o[NF - 1];
+      }
+    };
+    if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
+    else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
+    if (INMODE == IN_IMG_U8) __syncwarp();
+  }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -414,8 +661,11 @@ gauss_pass_x(const __grid_constant__ GaussCoef C, const __grid_constant__ PassAr
         A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
       }
     }
-    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, xs, i0, len, cs);
-    else forward_chunk<NF, L, FMA, true>(C, xs, i0, len, cs);
+    {
+      const RegSrc<NF, L> src{xs};
+      if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, src, i0, len, cs);
+      else forward_chunk<NF, L, FMA, true>(C, src, i0, len, cs);
+    }
   }
 
   Rec as[NF];
@@ -455,8 +705,13 @@ gauss_pass_x(const __grid_constant__ GaussCoef C, const __grid_constant__ PassAr
         cs[f].x3 = 0.0;
       }
     }
-    if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, xs, i0, len, n, cs, as);
-    else backward_chunk<NF, L, FMA, true>(C, xs, i0, len, n, cs, as);
+    {
+      // the sink overwrites xs[.][j] only after the anticausal step has consumed it
+      const RegSrc<NF, L> src{xs};
+      const RegSink<NF, L> sink{xs};
+      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
+      else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
+    }
     xtile_store<NF, L>(A, T, line0, i0, len, lane, xs);
   }
 }

@@ -60,6 +60,7 @@ def load_library():
     L.ife_cuda_reserve.argtypes = [vp, ip, i]
     L.ife_cuda_launch_count.argtypes = [vp]
     L.ife_cuda_launch_count.restype = C.c_uint64
+    L.ife_cuda_set_option.argtypes = [vp, C.c_char_p, i]
     L.ife_cuda_profile_enable.argtypes = [vp, i]
     L.ife_cuda_profile_read.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
     L.ife_cuda_gaussian.argtypes = [vp, vp, vp, ip, dp, d, i]
@@ -160,6 +161,9 @@ class Context:
 
     def set_stream(self, cuda_stream_handle):
         self._check(self.L.ife_cuda_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def set_option(self, name, value):
+        self._check(self.L.ife_cuda_set_option(self.h, name.encode(), int(value)))
 
     def synchronize(self):
         self._check(self.L.ife_cuda_synchronize(self.h))

@@ -88,6 +88,11 @@ int ife_cuda_reserve(ife_cuda_ctx* ctx, const int dims[3], int n_outputs);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx);
 
+/* Tuning / debugging switches.  "async_passes" (default 1): use the cp.async software-
+ * pipelined Gaussian pass kernels; 0 selects the plain register-staged kernels (same
+ * results bit for bit; kept as the fallback for layouts the pipelined kernels reject). */
+int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value);
+
 /* Optional per-kernel timing for benchmarks: while enabled, every kernel launch of the
  * context is bracketed by CUDA events on the launching stream.  ife_cuda_profile_read
  * synchronises, returns the summed device time (ms) and launch count per kernel kind since
