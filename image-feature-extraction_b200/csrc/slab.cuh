@@ -123,6 +123,127 @@ int ife_cuda_slab_halo(double sigma, double spacing_z, double halo_factor) {
   return (int)std::ceil(halo_factor * sigma / spacing_z) + 4 + 1;
 }
 
+// Per-rank compute on a buffer that already holds the owned planes plus halo: device
+// pointers bimg/bmask cover global planes [bz0, bz1); the rank owns [z0, z1).
+static int slab_compute(ife_cuda_ctx* ctx, const float* bimg, const uint8_t* bmask, int bz0, int bz1,
+                        int z0, int z1, float* out, const int global_dims[3],
+                        const double spacing[3], const double* sigmas, int n_sigma,
+                        const float* edges, int n_edges, uint32_t* counts, double halo_factor,
+                        int mem, uint32_t** d_counts_out) {
+  using namespace ife;
+  cudaStream_t st = ctx->stream();
+  Workspace& ws = ctx->ws;
+  const int nx = global_dims[0], ny = global_dims[1], nz = global_dims[2];
+  const size_t plane = (size_t)nx * ny;
+  const int nzo = z1 - z0, nzb = bz1 - bz0;
+  const size_t n_own = plane * nzo;
+  const int fz0 = std::max(0, z0 - 1), fz1 = std::min(nz, z1 + 1);  // planes the stencil reads
+  const int nzf = fz1 - fz0;
+  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nzb));
+  IFE_TRY(ws.blur.reserve(ctx, plane * nzf * sizeof(float)));
+  const int rows = n_sigma * 8, nb = n_edges + 1;
+  uint32_t* d_counts = nullptr;
+  if (edges) {
+    IFE_TRY(ws.edges.reserve(ctx, (size_t)rows * n_edges * sizeof(float)));
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ws.edges.ptr, edges, (size_t)rows * n_edges * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+    if (mem == IFE_MEM_HOST) {
+      IFE_TRY(ws.counts.reserve(ctx, (size_t)rows * nb * sizeof(uint32_t)));
+      d_counts = (uint32_t*)ws.counts.ptr;
+    } else {
+      d_counts = counts;
+    }
+    IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)rows * nb * sizeof(uint32_t), st));
+  }
+  if (d_counts_out) *d_counts_out = d_counts;
+  if (out && mem == IFE_MEM_HOST) IFE_TRY(ws.out[0].reserve(ctx, 8 * n_own * sizeof(float)));
+
+  const StencilCoef S = make_stencil_coef(spacing);
+  for (int s = 0; s < n_sigma; ++s) {
+    // z-pass extent at this scale: the warm-up halo shrinks with sigma
+    const int H = ife_cuda_slab_halo(sigmas[s], spacing[2], halo_factor);
+    const int sz0 = std::max(bz0, z0 - H), sz1 = std::min(bz1, z1 + H);
+    float* blur = (float*)ws.blur.ptr;
+    IFE_TRY(smooth_volume(ctx, bimg + plane * (sz0 - bz0), bmask + plane * (sz0 - bz0), true, blur, nx,
+                          ny, sz1 - sz0, fz0 - sz0, fz1 - sz0, spacing, sigmas[s], nullptr, nullptr));
+    FeatArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.vol = blur;
+    A.mask_u8 = bmask + plane * (fz0 - bz0);
+    A.nx = nx; A.ny = ny; A.nzb = nzf; A.zb0 = z0 - fz0; A.zb1 = A.zb0 + nzo; A.z_global0 = fz0;
+    float* d_out = nullptr;
+    if (out) {
+      d_out = mem == IFE_MEM_HOST ? (float*)ws.out[0].ptr : out + (size_t)s * 8 * n_own;
+      for (int k = 0; k < 8; ++k) A.out[k] = d_out + (size_t)k * n_own;
+    }
+    if (edges) {
+      A.hist.edges = (const float*)ws.edges.ptr + (size_t)s * 8 * n_edges;
+      A.hist.counts = d_counts + (size_t)s * 8 * nb;
+      A.hist.n_edges = n_edges;
+      A.hist.n_roi = 0;
+      A.hist.stride_roi = (long long)rows * nb;
+    }
+    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+    if (out && mem == IFE_MEM_HOST)
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n_own, d_out, 8 * n_own * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+  }
+  return IFE_OK;
+}
+
+static int slab_check_args(ife_cuda_ctx* ctx, const float* image, float* out, const int global_dims[3],
+                           const double spacing[3], const double* sigmas, int n_sigma,
+                           const float* edges, int n_edges, uint32_t* counts) {
+  using namespace ife;
+  if (!image) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  if (!out && !edges) return fail(ctx, IFE_E_INVALID, "nothing to compute: out and edges both null");
+  if (edges && (!counts || n_edges <= 0)) return fail(ctx, IFE_E_INVALID, "bad histogram arguments");
+  if (!sigmas || n_sigma <= 0) return fail(ctx, IFE_E_INVALID, "need at least one scale");
+  return check_dims(ctx, global_dims, spacing);
+}
+
+int ife_cuda_slab_emphysema_features_local(ife_cuda_ctx* ctx, const float* image_ext,
+                                           const uint8_t* mask_ext, int ext_z0, int ext_nz,
+                                           int own_z0, int own_nz, float* out,
+                                           const int global_dims[3], const double spacing[3],
+                                           const double* sigmas, int n_sigma, const float* edges,
+                                           int n_edges, uint32_t* counts, double halo_factor,
+                                           int mem) {
+  using namespace ife;
+  if (!ctx) return IFE_E_INVALID;
+  IFE_TRY(slab_check_args(ctx, image_ext, out, global_dims, spacing, sigmas, n_sigma, edges, n_edges, counts));
+  const int nz = global_dims[2];
+  if (own_nz <= 0 || own_z0 < 0 || own_z0 + own_nz > nz || ext_z0 < 0 || ext_z0 + ext_nz > nz ||
+      ext_z0 > own_z0 || ext_z0 + ext_nz < own_z0 + own_nz)
+    return fail(ctx, IFE_E_INVALID, "bad slab ranges");
+  // the buffer must reach one plane past the slab (central differences) unless at a global edge
+  if ((own_z0 > 0 && ext_z0 > own_z0 - 1) || (own_z0 + own_nz < nz && ext_z0 + ext_nz < own_z0 + own_nz + 1))
+    return fail(ctx, IFE_E_INVALID, "halo must cover at least one plane on every interior side");
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t plane = (size_t)global_dims[0] * global_dims[1];
+  const float* d_img;
+  const uint8_t* d_mask;
+  IFE_TRY(stage_in(ctx, ctx->ws.slab_img, image_ext, plane * ext_nz, mem, &d_img));
+  if (mask_ext) {
+    IFE_TRY(stage_in(ctx, ctx->ws.slab_mask, mask_ext, plane * ext_nz, mem, &d_mask));
+  } else {
+    IFE_TRY(ctx->ws.slab_mask.reserve(ctx, plane * ext_nz));
+    IFE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws.slab_mask.ptr, 1, plane * ext_nz, ctx->stream()));
+    d_mask = (const uint8_t*)ctx->ws.slab_mask.ptr;
+  }
+  uint32_t* d_counts = nullptr;
+  IFE_TRY(slab_compute(ctx, d_img, d_mask, ext_z0, ext_z0 + ext_nz, own_z0, own_z0 + own_nz, out,
+                       global_dims, spacing, sigmas, n_sigma, edges, n_edges, counts, halo_factor, mem,
+                       &d_counts));
+  if (mem == IFE_MEM_HOST) {
+    if (edges)
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)n_sigma * 8 * (n_edges + 1) * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
 int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
                                      const uint8_t* mask_slab, float* out,
                                      const int global_dims[3], const double spacing[3],
@@ -130,11 +251,7 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
                                      int n_edges, uint32_t* counts, double halo_factor, int mem) {
   using namespace ife;
   if (!ctx) return IFE_E_INVALID;
-  if (!image_slab) return fail(ctx, IFE_E_INVALID, "null image pointer");
-  if (!out && !edges) return fail(ctx, IFE_E_INVALID, "nothing to compute: out and edges both null");
-  if (edges && (!counts || n_edges <= 0)) return fail(ctx, IFE_E_INVALID, "bad histogram arguments");
-  if (!sigmas || n_sigma <= 0) return fail(ctx, IFE_E_INVALID, "need at least one scale");
-  IFE_TRY(check_dims(ctx, global_dims, spacing));
+  IFE_TRY(slab_check_args(ctx, image_slab, out, global_dims, spacing, sigmas, n_sigma, edges, n_edges, counts));
   const int P = ctx->n_ranks, me = ctx->rank;
   if (P > 1 && !ctx->nccl_comm) return fail(ctx, IFE_E_COMM, "communicator not initialised");
   IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -192,63 +309,17 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
     IFE_NCCL_TRY(ctx, api.GroupEnd());
   }
 
-  // ---- per-scale pipeline ----
-  const int fz0 = std::max(0, z0 - 1), fz1 = std::min(nz, z1 + 1);  // planes the stencil reads
-  const int nzf = fz1 - fz0;
-  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nzb));
-  IFE_TRY(ws.blur.reserve(ctx, plane * nzf * sizeof(float)));
-  const int rows = n_sigma * 8, nb = n_edges + 1;
   uint32_t* d_counts = nullptr;
-  if (edges) {
-    IFE_TRY(ws.edges.reserve(ctx, (size_t)rows * n_edges * sizeof(float)));
-    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ws.edges.ptr, edges, (size_t)rows * n_edges * sizeof(float),
-                                      cudaMemcpyHostToDevice, st));
-    if (mem == IFE_MEM_HOST) {
-      IFE_TRY(ws.counts.reserve(ctx, (size_t)rows * nb * sizeof(uint32_t)));
-      d_counts = (uint32_t*)ws.counts.ptr;
-    } else {
-      d_counts = counts;
-    }
-    IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)rows * nb * sizeof(uint32_t), st));
-  }
-  if (out && mem == IFE_MEM_HOST) IFE_TRY(ws.out[0].reserve(ctx, 8 * n_own * sizeof(float)));
-
-  const StencilCoef S = make_stencil_coef(spacing);
-  for (int s = 0; s < n_sigma; ++s) {
-    const int H = ife_cuda_slab_halo(sigmas[s], spacing[2], halo_factor);
-    const int sz0 = std::max(0, z0 - H), sz1 = std::min(nz, z1 + H);  // z-pass extent at this scale
-    float* blur = (float*)ws.blur.ptr;
-    IFE_TRY(smooth_volume(ctx, bimg + plane * (sz0 - bz0), bmask + plane * (sz0 - bz0), true, blur, nx,
-                          ny, sz1 - sz0, fz0 - sz0, fz1 - sz0, spacing, sigmas[s], nullptr, nullptr));
-    FeatArgs A;
-    std::memset(&A, 0, sizeof(A));
-    A.vol = blur;
-    A.mask_u8 = bmask + plane * (fz0 - bz0);
-    A.nx = nx; A.ny = ny; A.nzb = nzf; A.zb0 = z0 - fz0; A.zb1 = A.zb0 + nzo; A.z_global0 = fz0;
-    float* d_out = nullptr;
-    if (out) {
-      d_out = mem == IFE_MEM_HOST ? (float*)ws.out[0].ptr : out + (size_t)s * 8 * n_own;
-      for (int k = 0; k < 8; ++k) A.out[k] = d_out + (size_t)k * n_own;
-    }
-    if (edges) {
-      A.hist.edges = (const float*)ws.edges.ptr + (size_t)s * 8 * n_edges;
-      A.hist.counts = d_counts + (size_t)s * 8 * nb;
-      A.hist.n_edges = n_edges;
-      A.hist.n_roi = 0;
-      A.hist.stride_roi = (long long)rows * nb;
-    }
-    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
-    if (out && mem == IFE_MEM_HOST)
-      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n_own, d_out, 8 * n_own * sizeof(float),
-                                        cudaMemcpyDeviceToHost, st));
-  }
+  IFE_TRY(slab_compute(ctx, bimg, bmask, bz0, bz1, z0, z1, out, global_dims, spacing, sigmas, n_sigma,
+                       edges, n_edges, counts, halo_factor, mem, &d_counts));
 
   // ---- combine the per-rank histograms ----
   if (edges) {
+    const size_t n_counts = (size_t)n_sigma * 8 * (n_edges + 1);
     if (P > 1)
-      IFE_NCCL_TRY(ctx, api.AllReduce(d_counts, d_counts, (size_t)rows * nb, ncclUint32, ncclSum, comm, st));
+      IFE_NCCL_TRY(ctx, api.AllReduce(d_counts, d_counts, n_counts, ncclUint32, ncclSum, comm, st));
     if (mem == IFE_MEM_HOST)
-      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)rows * nb * sizeof(uint32_t),
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, n_counts * sizeof(uint32_t),
                                         cudaMemcpyDeviceToHost, st));
   }
   if (mem == IFE_MEM_HOST) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));

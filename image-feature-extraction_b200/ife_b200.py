@@ -78,6 +78,8 @@ def load_library():
     L.ife_cuda_slab_range.restype = None
     L.ife_cuda_slab_halo.argtypes = [d, d, d]
     L.ife_cuda_slab_emphysema_features.argtypes = [vp, vp, vp, vp, ip, dp, dp, i, vp, i, vp, d, i]
+    L.ife_cuda_slab_emphysema_features_local.argtypes = [vp, vp, vp, i, i, i, i, vp, ip, dp, dp, i, vp, i,
+                                                         vp, d, i]
     _lib = L
     return L
 
@@ -323,6 +325,27 @@ class Context:
         self._check(self.L.ife_cuda_slab_emphysema_features(
             self.h, _ptr(img_slab), _ptr(m), _ptr(out), _i3(global_dims), _d3(spacing),
             _dn(sigmas), len(sigmas), _ptr(e), n_edges, _ptr(counts), halo_factor, MEM_HOST))
+        return out, counts
+
+    def slab_emphysema_features_local(self, img_ext, mask_ext, ext_z0, own_z0, own_nz, global_dims,
+                                      sigmas, spacing=None, edges=None, want_features=True,
+                                      halo_factor=0.0):
+        """No communication: img_ext (ext_nz, ny, nx) holds global planes from ext_z0 on."""
+        img_ext = np.ascontiguousarray(img_ext, np.float32)
+        m = None if mask_ext is None else np.ascontiguousarray(mask_ext, np.uint8)
+        sigmas = list(sigmas)
+        shape = (own_nz,) + img_ext.shape[1:]
+        out = np.empty((len(sigmas), 8) + shape, np.float32) if want_features else None
+        e = counts = None
+        n_edges = 0
+        if edges is not None:
+            e = np.ascontiguousarray(edges, np.float32).reshape(len(sigmas) * 8, -1)
+            n_edges = e.shape[1]
+            counts = np.zeros((len(sigmas) * 8, n_edges + 1), np.uint32)
+        self._check(self.L.ife_cuda_slab_emphysema_features_local(
+            self.h, _ptr(img_ext), _ptr(m), ext_z0, img_ext.shape[0], own_z0, own_nz, _ptr(out),
+            _i3(global_dims), _d3(spacing), _dn(sigmas), len(sigmas), _ptr(e), n_edges, _ptr(counts),
+            halo_factor, MEM_HOST))
         return out, counts
 
     def slab_emphysema_features_dev(self, img_ptr, mask_ptr, out_ptr, global_dims, sigmas,

@@ -207,6 +207,21 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
                                      int n_edges, uint32_t* counts, double halo_factor,
                                      int mem);
 
+/* The per-rank half of the call above without any communication: image_ext / mask_ext hold
+ * global planes [ext_z0, ext_z0+ext_nz), which must contain the owned planes
+ * [own_z0, own_z0+own_nz) plus whatever halo the caller has (at least one plane on every
+ * side that is not a global edge; the z recursion warms up over min(available, halo(sigma))
+ * planes).  counts are this slab's own (not reduced).  Lets a caller with its own transport
+ * (MPI, host staging, a single GPU walking over slabs of a volume larger than its memory)
+ * use the slab pipeline. */
+int ife_cuda_slab_emphysema_features_local(ife_cuda_ctx* ctx, const float* image_ext,
+                                           const uint8_t* mask_ext, int ext_z0, int ext_nz,
+                                           int own_z0, int own_nz, float* out,
+                                           const int global_dims[3], const double spacing[3],
+                                           const double* sigmas, int n_sigma, const float* edges,
+                                           int n_edges, uint32_t* counts, double halo_factor,
+                                           int mem);
+
 #ifdef __cplusplus
 }
 #endif

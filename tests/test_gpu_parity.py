@@ -317,3 +317,58 @@ def test_full_size_invariants_512x512x400(ctx):
     for k in (0, 1, 2, 7):
         ref = np.bincount(np.searchsorted(edges[k], out[k][inside], side="left"), minlength=41)
         assert np.array_equal(counts[0, k], ref)
+
+
+# ------------------------------------------------------------------------------ z-slabs (one GPU)
+def test_slab_single_rank_equals_whole_volume(ctx):
+    shape = (40, 36, 44)
+    img = synth.ct_like(shape, seed=14, n_blobs=8)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    sigmas = [0.6, 2.4]
+    whole = ctx.emphysema_features(img, mask, sigmas)
+    edges = np.stack([synth.equalized_edges(whole[s, k][mask != 0], 20) for s in range(2) for k in range(8)])
+    out, counts = ctx.slab_emphysema_features(img, mask, (44, 36, 40), sigmas, edges=edges)
+    assert bits_equal(out, whole)
+    assert np.array_equal(counts, ctx.emphysema_histograms(img, mask, sigmas, edges)[0])
+
+
+@pytest.mark.parametrize("halo_factor,exact", [(0.0, False), (1000.0, True)])
+def test_slab_local_pipeline_matches_whole_volume(ctx, halo_factor, exact):
+    """Walk a volume slab by slab with ife_cuda_slab_emphysema_features_local (no NCCL): with a
+    halo that reaches the volume ends the result is bit-identical; with the default halo
+    (12 sigma + 5 planes) the truncated warm-up of the z recursion may move a blur value by
+    an ulp, which the eigenvalues see at <= 1e-4 * max|lambda| (asserted)."""
+    import ife_b200
+    shape = (96, 40, 48)
+    nz = shape[0]
+    img = synth.ct_like(shape, seed=15, n_blobs=20)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    sigmas = [0.6, 1.2]
+    whole = ctx.emphysema_features(img, mask, sigmas)
+    edges = np.stack([synth.equalized_edges(whole[s, k][mask != 0], 20) for s in range(2) for k in range(8)])
+    whole_counts = ctx.emphysema_histograms(img, mask, sigmas, edges)[0]
+    parts, total = [], np.zeros_like(whole_counts)
+    P = 3
+    for r in range(P):
+        z0, z1 = ife_b200.slab_range(nz, P, r)
+        H = ife_b200.slab_halo(max(sigmas), 1.0, halo_factor if halo_factor > 0 else 12.0)
+        e0, e1 = max(0, z0 - H), min(nz, z1 + H)
+        out, counts = ctx.slab_emphysema_features_local(img[e0:e1], mask[e0:e1], e0, z0, z1 - z0,
+                                                        (shape[2], shape[1], nz), sigmas, edges=edges,
+                                                        halo_factor=halo_factor)
+        parts.append(out)
+        total += counts
+    got = np.concatenate(parts, axis=2)
+    assert got.shape == whole.shape
+    if exact:
+        assert bits_equal(got, whole)
+        assert np.array_equal(total, whole_counts)
+    else:
+        n, worst = mismatch_report(got, whole)
+        print("default halo: %d of %d values differ from the whole-volume run (max abs %.3g)" % (n, got.size, worst))
+        assert np.all(total.sum(1) == mask.sum())
+        blur_err = np.abs(got[:, 0].astype(np.float64) - whole[:, 0])
+        assert blur_err.max() <= 2.5e-4            # a few float ulps at ~1000 HU
+        lam = np.abs(whole[:, 2:5]).max(1)
+        err = np.abs(got[:, 2:5].astype(np.float64) - whole[:, 2:5]).max(1)
+        assert np.mean(err > TOL * lam + 1e-3) < 1e-3

@@ -1,0 +1,97 @@
+"""Multi-GPU tests.  GPU part: the NCCL z-slab path on >= 2 GPUs (skipped on a 1-GPU box).
+CPU part: the same partition / halo / all-reduce protocol exercised with world_size-2 gloo
+processes, the oracle standing in for the kernels."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_nccl_slab_path_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    line = [l for l in proc.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
+    res = json.loads(line[len("MGPU_RESULT "):])
+    print(res)
+    assert res["full_halo"]["max_mismatching_values_per_rank"] == 0      # bit-identical to one GPU
+    assert res["full_halo"]["hist_abs_diff_vs_whole"] == 0
+    assert res["default_halo"]["max_abs_diff"] < 1.0
+
+
+def _gloo_worker(rank, world, port, shape, sigma, halo, q):
+    import torch.distributed as dist
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "image-feature-extraction_b200"))
+    import oracle as O
+    import ife_b200
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nz = shape[0]
+    img = synth.ct_like(shape, seed=41, n_blobs=10)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    z0, z1 = ife_b200.slab_range(nz, world, rank)
+    own = torch.from_numpy(img[z0:z1].copy())
+    b0, b1 = max(0, z0 - halo), min(nz, z1 + halo)
+    buf = torch.zeros((b1 - b0,) + shape[1:])
+    buf[z0 - b0:z1 - b0] = own
+    # halo exchange with every rank whose slab intersects [b0, b1) (same loop as slab.cuh)
+    reqs = []
+    for r in range(world):
+        if r == rank:
+            continue
+        r0, r1 = ife_b200.slab_range(nz, world, r)
+        n0, n1 = max(b0, r0), min(b1, r1)
+        if n0 < n1:
+            reqs.append(dist.irecv(buf[n0 - b0:n1 - b0], src=r))
+        rb0, rb1 = max(0, r0 - halo), min(nz, r1 + halo)
+        s0, s1 = max(rb0, z0), min(rb1, z1)
+        if s0 < s1:
+            reqs.append(dist.isend(own[s0 - z0:s1 - z0].contiguous(), dst=r))
+    for rq in reqs:
+        rq.wait()
+    ext = buf.numpy()
+    assert np.array_equal(ext, img[b0:b1])                      # halos arrived where they belong
+    f = O.emphysema_features(ext, mask[b0:b1], sigma, threads=1)[:, z0 - b0:z1 - b0]
+    whole = O.emphysema_features(img, mask, sigma, threads=1)
+    edges = np.stack([synth.equalized_edges(whole[k][mask != 0], 12) for k in range(8)])
+    counts = torch.from_numpy(O.features_histograms(f, mask[z0:z1], edges)[0].astype(np.int64))
+    dist.all_reduce(counts)                                     # histogram all-reduce
+    whole_counts = O.features_histograms(whole, mask, edges)[0].astype(np.int64)
+    q.put((rank, float(np.abs(f - whole[:, z0:z1]).max()), int(np.abs(counts.numpy() - whole_counts).sum()),
+           int(counts.sum()), int(8 * mask.sum())))
+    dist.destroy_process_group()
+
+
+def test_slab_protocol_gloo_world2():
+    """world_size 2 on CPU (gloo): slab ranges tile the volume, halos land in the right planes,
+    per-slab features with a halo reaching the volume ends equal the whole-volume oracle, and
+    the all-reduced histogram equals the whole-volume histogram."""
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    shape, world = (40, 12, 14), 2
+    procs = [ctxm.Process(target=_gloo_worker, args=(r, world, 29547, shape, 1.0, 1000, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, hist_diff, total, expect in out:
+        assert err == 0.0 and hist_diff == 0 and total == expect
