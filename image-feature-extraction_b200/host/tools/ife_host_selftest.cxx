@@ -1,0 +1,48 @@
+// Host-side self test that needs no GPU: command-line parsing, Path::join, NIfTI round trip.
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+
+#include "ife/IO/NiftiIO.h"
+#include "ife/Util/CmdLine.h"
+#include "ife/Util/Path.h"
+
+#define CHECK(c) do { if (!(c)) { std::cerr << "FAILED: " #c << " (line " << __LINE__ << ")" << std::endl; return 1; } } while (0)
+
+int main(int argc, char* argv[]) {
+  CHECK(ife::Path::join("a/b//", "/c.nii") == "a/b/c.nii");
+  CHECK(ife::Path::join("", "x") == "/x");
+  CHECK(ife::Path::join("out", "") == "out/");
+  {
+    ife::CmdLine cmd("t", "0.1");
+    cmd.add("i", "image", "", true, "", "path");
+    cmd.add("s", "scale", "", true, "", "double", true);
+    cmd.add("p", "prefix", "", false, "def_", "string");
+    const char* av[] = {"tool", "-i", "a.nii", "--scale", "0.6", "-s", "1.2", "--scale=2.4"};
+    int rc = -1;
+    CHECK(cmd.parse(8, const_cast<char**>(av), &rc));
+    CHECK(cmd.value("image") == "a.nii" && cmd.values("scale").size() == 3 && cmd.value("prefix") == "def_");
+    float f;
+    CHECK(ife::CmdLine::convert(cmd.values("scale")[2], &f) && f == 2.4f);
+    CHECK(std::to_string(0.6f) == "0.600000");
+  }
+  const std::string dir = argc > 1 ? argv[1] : "/tmp";
+  auto img = ife::Image<float>::New();
+  img->SetRegions(5, 4, 3);
+  img->SetSpacing(0.7, 0.8, 2.5);
+  img->Allocate();
+  for (size_t i = 0; i < img->GetNumberOfPixels(); ++i) img->GetBufferPointer()[i] = (float)i * 0.5f - 7;
+  for (const char* ext : {".nii", ".nii.gz"}) {
+    const std::string p = ife::Path::join(dir, std::string("ife_selftest") + ext);
+    ife::nifti::Write(p, *img);
+    auto back = ife::nifti::Read<float>(p);
+    CHECK(back->GetSize() == img->GetSize());
+    CHECK(std::fabs(back->GetSpacing()[2] - 2.5) < 1e-6 && std::fabs(back->GetSpacing()[0] - 0.7) < 1e-6);
+    CHECK(back->GetPixelContainer() == img->GetPixelContainer());
+    auto as_u8 = ife::nifti::Read<unsigned char>(p);   // cast on read, like itk::ImageFileReader
+    CHECK(as_u8->GetPixel(4, 3, 2) == (unsigned char)(59 * 0.5f - 7));
+    std::remove(p.c_str());
+  }
+  std::cout << "host selftest ok" << std::endl;
+  return 0;
+}
