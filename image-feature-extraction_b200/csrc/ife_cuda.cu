@@ -181,11 +181,12 @@ template <int NF, int INMODE, bool DIVIDE>
 int launch_strided(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
   const unsigned grid = (unsigned)((A.n_lines + 127) / 128);
   ProfScope prof(ctx, A.stride == (long long)A.na && A.sb == 0 ? K_PASS_Z : K_PASS_Y);
-  // software-pipelined kernel unless the uint8 mask cannot be moved in aligned 4-byte pieces
-  bool async_ok = ctx->use_async;
-  if (INMODE == IN_IMG_U8)
-    async_ok = async_ok && A.sb == 0 && (reinterpret_cast<uintptr_t>(A.in1) % 4 == 0) &&
-               A.stride % 4 == 0 && A.n_lines % 4 == 0;
+  // software-pipelined kernel when every warp's 32 lines are contiguous and 16-byte aligned
+  const bool contiguous = A.sb == 0 || A.na % 32 == 0;   // no warp straddles two line groups
+  bool async_ok = ctx->use_async && contiguous && A.n_lines % 4 == 0 && A.stride % 4 == 0 &&
+                  (A.sb % 4 == 0) && reinterpret_cast<uintptr_t>(A.in0) % 16 == 0 &&
+                  (NF == 1 || reinterpret_cast<uintptr_t>(A.in1) % 16 == 0);
+  if (INMODE == IN_IMG_U8) async_ok = async_ok && A.stride % 16 == 0 && A.n_lines % 16 == 0;
   if (async_ok) {
     if (ctx->arith == IFE_ARITH_FMA) IFE_TRY((launch_strided_async<NF, INMODE, DIVIDE, true>(ctx, C, A)));
     else IFE_TRY((launch_strided_async<NF, INMODE, DIVIDE, false>(ctx, C, A)));
@@ -199,15 +200,34 @@ int launch_strided(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
   return IFE_OK;
 }
 
+template <int NF, bool FMA>
+int launch_x_async(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
+  auto kern = gauss_pass_x_async<NF, kChunk, FMA, kXWarps, kAsyncStages>;
+  const size_t smem = kXWarps * (kAsyncStages * sizeof(XStage<NF, kChunk>) + sizeof(XOut<NF, kChunk>));
+  IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long lines_per_block = 32LL * kXWarps;
+  const unsigned grid = (unsigned)((A.n_lines + lines_per_block - 1) / lines_per_block);
+  kern<<<grid, 32 * kXWarps, smem, ctx->stream()>>>(C, A);
+  return IFE_OK;
+}
+
 template <int NF>
 int launch_x(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
   const long long lines_per_block = 32LL * kXWarps;
   const unsigned grid = (unsigned)((A.n_lines + lines_per_block - 1) / lines_per_block);
   ProfScope prof(ctx, K_PASS_X);
-  if (ctx->arith == IFE_ARITH_FMA)
+  const bool async_ok = ctx->use_async && A.n % 4 == 0 && reinterpret_cast<uintptr_t>(A.in0) % 16 == 0 &&
+                        reinterpret_cast<uintptr_t>(A.out0) % 16 == 0 &&
+                        (NF == 1 || (reinterpret_cast<uintptr_t>(A.in1) % 16 == 0 &&
+                                     reinterpret_cast<uintptr_t>(A.out1) % 16 == 0));
+  if (async_ok) {
+    if (ctx->arith == IFE_ARITH_FMA) IFE_TRY((launch_x_async<NF, true>(ctx, C, A)));
+    else IFE_TRY((launch_x_async<NF, false>(ctx, C, A)));
+  } else if (ctx->arith == IFE_ARITH_FMA) {
     gauss_pass_x<NF, kChunk, true, kXWarps><<<grid, 32 * kXWarps, 0, ctx->stream()>>>(C, A);
-  else
+  } else {
     gauss_pass_x<NF, kChunk, false, kXWarps><<<grid, 32 * kXWarps, 0, ctx->stream()>>>(C, A);
+  }
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
   return IFE_OK;

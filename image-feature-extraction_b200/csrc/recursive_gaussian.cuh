@@ -364,14 +364,12 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
 // Strided lines, software-pipelined: the same sweep as gauss_pass_strided, but every chunk
 // (its L samples, the 3 samples of causal history before it and, in phase B, its
 // checkpoint) is brought into shared memory with cp.async STAGES-1 chunks ahead of its use.
-// Each thread copies exactly the bytes its own line needs into a slot only it reads, so no
-// block barrier is needed: cp.async.wait_group orders a thread's copies before its own
-// reads.  (The uint8 mask is the one exception: cp.async moves at least 4 bytes, so every
-// fourth lane copies the mask bytes of four adjacent lines and the warp synchronises.)
-// With 2 CTAs of 128 threads per SM and 3 stages, >100 KB per SM is in flight, which is what
-// hides HBM latency at the 8 resident warps the 200+ registers of the recurrence allow.
-// Requirements checked on the host (else the plain kernel runs): for IN_IMG_U8 the mask
-// pointer, the line stride and n_lines are multiples of 4.
+// A warp copies exactly the columns its own 32 lines need (see stage_issue), so no block
+// barrier exists anywhere: cp.async.wait_group + __syncwarp order a warp's copies before
+// its reads.  With 2 CTAs of 128 threads per SM and 3 stages, >100 KB per SM is in flight,
+// which is what hides HBM latency at the 8 resident warps the 200+ registers of the
+// recurrence allow.  Alignment requirements are checked on the host (else the plain
+// register-staged kernel runs).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -412,38 +410,58 @@ __device__ __forceinline__ void stage_sample(const AsyncStage<NF, INMODE, L>& S,
   }
 }
 
-// issue the copies of chunk kc (planes i0-3+row_first .. i0+len-1) into stage S
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+// Issue the copies of chunk kc (planes i0-3+row_first .. i0+L-1, clipped to the line) into
+// stage S.  Warp-cooperative 16-byte copies: a warp's 32 lines are 128 contiguous bytes per
+// plane, so one cp.async.cg instruction (32 lanes x 16 B) moves 4 planes of a float field
+// (16 planes of the uint8 mask) -- 5 instructions per field per chunk instead of 19 per
+// thread.  The data a thread reads was copied by other lanes of ITS OWN warp, so a
+// __syncwarp after cp.async.wait_group is all the synchronisation needed.
+// Host-checked: every warp's 32 lines are contiguous in memory (line stride 1, no wrap),
+// pointers and plane strides are 16-byte aligned, n_lines % 4 == 0 (% 16 with a uint8 mask).
 template <int NF, int INMODE, int L>
 __device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, INMODE, L>& S, int t,
-                                            bool active, size_t base, size_t line, int kc,
-                                            int row_first, bool with_ckpt) {
+                                            size_t wbase, long long wline, size_t line, bool active,
+                                            int kc, int row_first, bool with_ckpt) {
   constexpr int ROWS = L + 3;
+  const int lane = t & 31, wcol = t & ~31;
   const int i0 = kc * L;
-  if (active) {
+  const size_t st = (size_t)A.stride;
+  {
+    const int q = lane >> 3, c = lane & 7;              // 4 planes x 8 chunks of 4 floats
+    const bool grp_ok = wline + 4 * c < A.n_lines;
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
+    for (int m = 0; m < (ROWS + 3) / 4; ++m) {
+      const int r = 4 * m + q;
       const int plane = i0 - 3 + r;
-      if (r >= row_first && plane >= 0 && plane < A.n) {
-        const size_t idx = base + (size_t)plane * (size_t)A.stride;
-        cp_async4(&S.f0[r][t], A.in0 + idx);
-        if (NF == 2) {
-          if (INMODE == IN_IMG_U8) {
-            if ((t & 3) == 0)
-              cp_async4(reinterpret_cast<uint8_t*>(&S.f1[0][0]) + r * kAsyncThreads + t,
-                        reinterpret_cast<const uint8_t*>(A.in1) + idx);
-          } else {
-            cp_async4(&S.f1[NF == 2 ? r : 0][t], reinterpret_cast<const float*>(A.in1) + idx);
-          }
-        }
+      if (r < ROWS && r >= row_first && plane >= 0 && plane < A.n && grp_ok) {
+        const size_t idx = wbase + (size_t)plane * st + 4 * c;
+        cp_async16(&S.f0[r][wcol + 4 * c], A.in0 + idx);
+        if (NF == 2 && INMODE != IN_IMG_U8)
+          cp_async16(&S.f1[NF == 2 ? r : 0][wcol + 4 * c], reinterpret_cast<const float*>(A.in1) + idx);
       }
     }
-    if (with_ckpt && kc >= 1) {
+  }
+  if (NF == 2 && INMODE == IN_IMG_U8) {
+    const int q = lane >> 1, h = lane & 1;              // 16 planes x 2 chunks of 16 bytes
+    const bool grp_ok = wline + 16 * h < A.n_lines;
+    uint8_t* m8 = reinterpret_cast<uint8_t*>(&S.f1[0][0]);
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          cp_async8(&S.ck[f * 4 + k][t], A.ckpt + ckpt_index<NF>(kc, f, k, A.n_lines, line));
+    for (int m = 0; m < (ROWS + 15) / 16; ++m) {
+      const int r = 16 * m + q;
+      const int plane = i0 - 3 + r;
+      if (r < ROWS && r >= row_first && plane >= 0 && plane < A.n && grp_ok)
+        cp_async16(m8 + r * kAsyncThreads + wcol + 16 * h,
+                   reinterpret_cast<const uint8_t*>(A.in1) + wbase + (size_t)plane * st + 16 * h);
     }
+  }
+  if (with_ckpt && kc >= 1 && active) {
+    const double* src = A.ckpt + ckpt_index<NF>(kc, 0, 0, A.n_lines, line);
+#pragma unroll
+    for (int k = 0; k < NF * 4; ++k) cp_async8(&S.ck[k][t], src + (size_t)k * (size_t)A.n_lines);
   }
   cp_async_commit();
 }
@@ -459,6 +477,10 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   const bool active = line_ll < A.n_lines;
   const size_t line = (size_t)(active ? line_ll : A.n_lines - 1);
   const size_t base = (size_t)(line % A.na) + (size_t)(line / A.na) * (size_t)A.sb;
+  // first line of this warp (its 32 lines are contiguous in memory: host-checked)
+  const long long wline = line_ll - (t & 31);
+  const long long wl = wline < A.n_lines ? wline : A.n_lines - 1;
+  const size_t wbase = (size_t)(wl % A.na) + (size_t)(wl / A.na) * (size_t)A.sb;
   const size_t st = (size_t)A.stride;
   const int n = A.n;
   const int n_chunks = (n + L - 1) / L;
@@ -469,15 +491,15 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   // ---- phase A: causal sweep, checkpoint at every chunk start ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < n_chunks) stage_issue<NF, INMODE, L>(A, stages[s], t, active, base, line, s, 3, false);
+    if (s < n_chunks) stage_issue<NF, INMODE, L>(A, stages[s], t, wbase, wline, line, active, s, 3, false);
     else cp_async_commit();
   }
   for (int k = 0; k < n_chunks; ++k) {
     const int kn = k + STAGES - 1;
-    if (kn < n_chunks) stage_issue<NF, INMODE, L>(A, stages[kn % STAGES], t, active, base, line, kn, 3, false);
+    if (kn < n_chunks) stage_issue<NF, INMODE, L>(A, stages[kn % STAGES], t, wbase, wline, line, active, kn, 3, false);
     else cp_async_commit();
     cp_async_wait<STAGES - 1>();
-    if (INMODE == IN_IMG_U8) __syncwarp();
+    __syncwarp();
     const Stage& S = stages[k % STAGES];
     const int i0 = k * L;
     const int len = min(L, n - i0);
@@ -504,7 +526,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 #pragma unroll
       for (int f = 0; f < NF; ++f) rec_fill(as[f], v[f]);
     }
-    if (INMODE == IN_IMG_U8) __syncwarp();  // mask bytes are shared by 4 lanes: all reads done
+    __syncwarp();  // every lane is done with this stage before any lane refills it
   }
   cp_async_wait<0>();
   __threadfence_block();
@@ -513,17 +535,17 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     const int kc = n_chunks - 1 - s;
-    if (kc >= 0) stage_issue<NF, INMODE, L>(A, stages[s], t, active, base, line, kc, 0, true);
+    if (kc >= 0) stage_issue<NF, INMODE, L>(A, stages[s], t, wbase, wline, line, active, kc, 0, true);
     else cp_async_commit();
   }
   for (int q = 0; q < n_chunks; ++q) {
     const int k = n_chunks - 1 - q;
     const int qn = q + STAGES - 1;
     if (qn < n_chunks)
-      stage_issue<NF, INMODE, L>(A, stages[qn % STAGES], t, active, base, line, n_chunks - 1 - qn, 0, true);
+      stage_issue<NF, INMODE, L>(A, stages[qn % STAGES], t, wbase, wline, line, active, n_chunks - 1 - qn, 0, true);
     else cp_async_commit();
     cp_async_wait<STAGES - 1>();
-    if (INMODE == IN_IMG_U8) __syncwarp();
+    __syncwarp();
     const Stage& S = stages[q % STAGES];
     const int i0 = k * L;
     const int len = min(L, n - i0);
@@ -566,7 +588,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     };
     if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
     else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
-    if (INMODE == IN_IMG_U8) __syncwarp();
+    __syncwarp();
   }
   cp_async_wait<0>();
 }
@@ -714,6 +736,210 @@ gauss_pass_x(const __grid_constant__ GaussCoef C, const __grid_constant__ PassAr
     }
     xtile_store<NF, L>(A, T, line0, i0, len, lane, xs);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// x pass, software-pipelined.  A warp owns 32 adjacent lines.  Chunk k of those lines is a
+// [32 lines] x [16 floats] tile (64 contiguous bytes per line); it is brought in by 4
+// cp.async.cg instructions per field in which four lanes cover one line's 64 bytes
+// (coalesced, every sector fully used), STAGES-1 chunks ahead.  In shared memory the four
+// 16-byte pieces of a line are XOR-swizzled with (line >> 1) & 3, which makes BOTH access
+// patterns conflict-free: the cooperative side (4 lanes per line) and the per-line side
+// (lane = line reads its 64 bytes with four LDS.128).  Results leave the same way in
+// reverse through a per-warp output tile.  Only __syncwarp is ever needed.
+// Host-checked: nx % 4 == 0, 16-byte aligned pointers.
+// ---------------------------------------------------------------------------------------
+template <int NF, int L>
+struct XStage {
+  float tile[NF][32][L];        // swizzled in 16-byte pieces
+  float hist[NF][32][4];        // samples i0-4 .. i0-1 of every line (phase B)
+  double ck[NF * 4][32];
+};
+template <int NF, int L>
+struct XOut {
+  float tile[NF][32][L];
+};
+
+__device__ __forceinline__ int xswz(int line, int piece) { return piece ^ ((line >> 1) & 3); }
+
+template <int NF, int L>
+__device__ __forceinline__ void xstage_issue(const PassArgs& A, XStage<NF, L>& S, int lane,
+                                             long long line0, int kc, bool with_hist_ckpt) {
+  static_assert(L == 16, "one chunk = four 16-byte pieces per line");
+  const int i0 = kc * L;
+  const int piece = lane & 3;
+  const bool col_ok = i0 + 4 * piece < A.n;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int ll = (lane >> 2) + 8 * m;
+    const long long gl = line0 + ll;
+    if (gl < A.n_lines && col_ok) {
+      const size_t idx = (size_t)gl * (size_t)A.n + (size_t)(i0 + 4 * piece);
+      cp_async16(&S.tile[0][ll][4 * xswz(ll, piece)], A.in0 + idx);
+      if (NF == 2) cp_async16(&S.tile[NF - 1][ll][4 * xswz(ll, piece)], reinterpret_cast<const float*>(A.in1) + idx);
+    }
+  }
+  if (with_hist_ckpt && kc >= 1) {
+    const long long gl = line0 + lane;
+    if (gl < A.n_lines) {
+      const size_t idx = (size_t)gl * (size_t)A.n + (size_t)(i0 - 4);
+      cp_async16(&S.hist[0][lane][0], A.in0 + idx);
+      if (NF == 2) cp_async16(&S.hist[NF - 1][lane][0], reinterpret_cast<const float*>(A.in1) + idx);
+      const double* src = A.ckpt + ckpt_index<NF>(kc, 0, 0, A.n_lines, (size_t)gl);
+#pragma unroll
+      for (int k = 0; k < NF * 4; ++k) cp_async8(&S.ck[k][lane], src + (size_t)k * (size_t)A.n_lines);
+    }
+  }
+  cp_async_commit();
+}
+
+template <int NF, int L>
+__device__ __forceinline__ void xstage_read(const XStage<NF, L>& S, int lane, float (&xs)[NF][L]) {
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(&S.tile[f][lane][4 * xswz(lane, p)]);
+      xs[f][4 * p + 0] = v.x; xs[f][4 * p + 1] = v.y; xs[f][4 * p + 2] = v.z; xs[f][4 * p + 3] = v.w;
+    }
+}
+
+template <int NF, int L, bool FMA, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32)
+gauss_pass_x_async(const __grid_constant__ GaussCoef C, const __grid_constant__ PassArgs A) {
+  extern __shared__ __align__(16) unsigned char xasync_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  XStage<NF, L>* stages = reinterpret_cast<XStage<NF, L>*>(xasync_smem) + warp * STAGES;
+  XOut<NF, L>& O = reinterpret_cast<XOut<NF, L>*>(reinterpret_cast<XStage<NF, L>*>(xasync_smem) + WARPS * STAGES)[warp];
+  const long long line0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+  if (line0 >= A.n_lines) return;   // whole warp exits together
+  const long long line = line0 + lane;
+  const bool active = line < A.n_lines;
+  const int n = A.n;
+  const int n_chunks = (n + L - 1) / L;
+
+  float xs[NF][L];
+  Rec cs[NF];
+  Rec as[NF];
+
+  // ---- phase A ----
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < n_chunks) xstage_issue<NF, L>(A, stages[s], lane, line0, s, false);
+    else cp_async_commit();
+  }
+  for (int k = 0; k < n_chunks; ++k) {
+    const int kn = k + STAGES - 1;
+    if (kn < n_chunks) xstage_issue<NF, L>(A, stages[kn % STAGES], lane, line0, kn, false);
+    else cp_async_commit();
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    xstage_read<NF, L>(stages[k % STAGES], lane, xs);
+    __syncwarp();
+    const int i0 = k * L;
+    const int len = min(L, n - i0);
+    if (k == 0) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) rec_fill(cs[f], (double)xs[f][0]);
+    } else if (active) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        A.ckpt[ckpt_index<NF>(k, f, 0, A.n_lines, line)] = cs[f].h0;
+        A.ckpt[ckpt_index<NF>(k, f, 1, A.n_lines, line)] = cs[f].h1;
+        A.ckpt[ckpt_index<NF>(k, f, 2, A.n_lines, line)] = cs[f].h2;
+        A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
+      }
+    }
+    {
+      const RegSrc<NF, L> src{xs};
+      if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, src, i0, len, cs);
+      else forward_chunk<NF, L, FMA, true>(C, src, i0, len, cs);
+    }
+    if (k == n_chunks - 1) {
+      float vlast[NF];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) vlast[f] = xs[f][0];
+#pragma unroll
+      for (int j = 1; j < L; ++j)
+        if (j < len) {
+#pragma unroll
+          for (int f = 0; f < NF; ++f) vlast[f] = xs[f][j];
+        }
+#pragma unroll
+      for (int f = 0; f < NF; ++f) rec_fill(as[f], (double)vlast[f]);
+    }
+  }
+  cp_async_wait<0>();
+  __threadfence_block();
+
+  // ---- phase B ----
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    const int kc = n_chunks - 1 - s;
+    if (kc >= 0) xstage_issue<NF, L>(A, stages[s], lane, line0, kc, true);
+    else cp_async_commit();
+  }
+  for (int q = 0; q < n_chunks; ++q) {
+    const int k = n_chunks - 1 - q;
+    const int qn = q + STAGES - 1;
+    if (qn < n_chunks) xstage_issue<NF, L>(A, stages[qn % STAGES], lane, line0, n_chunks - 1 - qn, true);
+    else cp_async_commit();
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const XStage<NF, L>& S = stages[q % STAGES];
+    xstage_read<NF, L>(S, lane, xs);
+    const int i0 = k * L;
+    const int len = min(L, n - i0);
+    if (k == 0) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) rec_fill(cs[f], (double)xs[f][0]);
+    } else {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float4 h = *reinterpret_cast<const float4*>(&S.hist[f][lane][0]);
+        cs[f].h0 = S.ck[f * 4 + 0][lane];
+        cs[f].h1 = S.ck[f * 4 + 1][lane];
+        cs[f].h2 = S.ck[f * 4 + 2][lane];
+        cs[f].h3 = S.ck[f * 4 + 3][lane];
+        cs[f].x0 = (double)h.w;
+        cs[f].x1 = (double)h.z;
+        cs[f].x2 = (double)h.y;
+        cs[f].x3 = 0.0;
+      }
+    }
+    __syncwarp();   // stage fully consumed by every lane before any lane refills it
+    {
+      const RegSrc<NF, L> src{xs};
+      const RegSink<NF, L> sink{xs};
+      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
+      else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
+    }
+    // results -> swizzled output tile -> coalesced 16-byte stores
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        *reinterpret_cast<float4*>(&O.tile[f][lane][4 * xswz(lane, p)]) =
+            make_float4(xs[f][4 * p], xs[f][4 * p + 1], xs[f][4 * p + 2], xs[f][4 * p + 3]);
+    __syncwarp();
+    {
+      const int piece = lane & 3;
+      const bool col_ok = i0 + 4 * piece < n;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int ll = (lane >> 2) + 8 * m;
+        const long long gl = line0 + ll;
+        if (gl < A.n_lines && col_ok) {
+          const size_t idx = (size_t)gl * (size_t)n + (size_t)(i0 + 4 * piece);
+          *reinterpret_cast<float4*>(A.out0 + idx) = *reinterpret_cast<const float4*>(&O.tile[0][ll][4 * xswz(ll, piece)]);
+          if (NF == 2)
+            *reinterpret_cast<float4*>(A.out1 + idx) = *reinterpret_cast<const float4*>(&O.tile[NF - 1][ll][4 * xswz(ll, piece)]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
 }
 
 }  // namespace ife
