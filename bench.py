@@ -111,7 +111,7 @@ def synth_scan_torch(torch, device, seed, mask_kind):
     return img, mask
 
 
-def run_reference(args):
+def run_reference(args, out_stream):
     """--impl reference: the reference's CPU path (oracle port; ITK itself cannot be built in
     this image) on this box's host cores, same metric/config, each step a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -141,7 +141,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     val = units / dt / 1e9
     sample = "%dx%dx%d sub-volume x %d scales per step" % (nx, ny, REF_STEP_NZ, len(SIGMAS))
-    print(json.dumps({
+    out_stream.emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 recursion / f32 stencil+solver",
@@ -173,10 +173,38 @@ def cpu_baseline(torch, img_dev, mask_dev):
                       (DIMS[0], DIMS[1], CPU_SAMPLE_NZ, len(SIGMAS), dt)}
 
 
+class QuietStdout:
+    """Routes fd 1 to stderr while the benchmark runs (NCCL and friends print banners on
+    stdout) so that the JSON line is the ONLY thing this process writes to stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
+    with QuietStdout() as out:
+        _main(out)
+
+
+def _main(out_stream):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="extract", choices=["extract", "hist", "slab"])
@@ -186,7 +214,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_stream)
 
     import numpy as np
     import torch
@@ -339,7 +367,7 @@ def main():
         cpu = cpu_baseline(torch, img, mask)
 
     if rank == 0:
-        print(json.dumps({
+        out_stream.emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 recursion / f32 stencil+solver", "data": "synthetic",
