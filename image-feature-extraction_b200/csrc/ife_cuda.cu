@@ -167,14 +167,21 @@ size_t ckpt_bytes_volume(int nf, int nx, int ny, int nz) {
 
 constexpr int kAsyncStages = 3;
 
-template <int NF, int INMODE, bool DIVIDE, bool FMA>
-int launch_strided_async(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
-  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, kChunk, FMA, kAsyncStages>;
+template <int NF, int INMODE, bool DIVIDE, int MASKMODE, bool FMA>
+int launch_strided_async_m(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
+  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, MASKMODE, kChunk, FMA, kAsyncStages>;
   const size_t smem = sizeof(AsyncStage<NF, INMODE, kChunk>) * kAsyncStages;
   IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A.n_lines + kAsyncThreads - 1) / kAsyncThreads);
   kern<<<grid, kAsyncThreads, smem, ctx->stream()>>>(C, A);
   return IFE_OK;
+}
+
+template <int NF, int INMODE, bool DIVIDE, bool FMA>
+int launch_strided_async(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
+  if (DIVIDE && A.mask_u8) return launch_strided_async_m<NF, INMODE, DIVIDE, DIVIDE ? 1 : 0, FMA>(ctx, C, A);
+  if (DIVIDE && A.mask_f32) return launch_strided_async_m<NF, INMODE, DIVIDE, DIVIDE ? 2 : 0, FMA>(ctx, C, A);
+  return launch_strided_async_m<NF, INMODE, DIVIDE, 0, FMA>(ctx, C, A);
 }
 
 template <int NF, int INMODE, bool DIVIDE>

@@ -31,6 +31,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fdiv.cuh"
+
 namespace ife {
 
 // N0..N3 feed-forward (causal), D1..D4 feedback, M1..M4 feed-forward (anticausal),
@@ -205,7 +207,16 @@ struct RegSink {
 
 // itk::DivideImageFilter functor: b != 0 ? a/b : NumericTraits<float>::max()
 __device__ __forceinline__ float itk_divide(float a, float b) {
-  return b != 0.0f ? __fdiv_rn(a, b) : FLT_MAX;
+  if (b == 0.0f) return FLT_MAX;
+  // far from the mask both G(cT) and G(c) are tiny, down to denormals: scale both by 2^80
+  // (exact, the quotient is unchanged), twice if need be, so that they too take the
+  // branch-free division instead of the compiler's slow path
+  float as = a, bs = b;
+  if (fabsf(bs) < 0x1p-40f && fabsf(as) < 0x1p40f) { as *= 0x1p80f; bs *= 0x1p80f; }
+  if (fabsf(bs) < 0x1p-40f && fabsf(as) < 0x1p40f) { as *= 0x1p80f; bs *= 0x1p80f; }
+  const float mb = fabsf(bs);
+  if (mb > 0x1p-40f && mb < 0x1p40f && div_safe_num(as)) return div_with_rcp(as, bs, __frcp_rn(bs));
+  return __fdiv_rn(a, b);
 }
 
 struct PassArgs {
@@ -466,7 +477,8 @@ __device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, IN
   cp_async_commit();
 }
 
-template <int NF, int INMODE, bool DIVIDE, int L, bool FMA, int STAGES>
+// MASKMODE (DIVIDE only): 0 = no output mask, 1 = uint8 mask, 2 = float mask
+template <int NF, int INMODE, bool DIVIDE, int MASKMODE, int L, bool FMA, int STAGES>
 __global__ void __launch_bounds__(kAsyncThreads)
 gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_constant__ PassArgs A) {
   using Stage = AsyncStage<NF, INMODE, L>;
@@ -574,14 +586,15 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     const size_t obase = base + (size_t)i0 * st;
     auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L>(S, 3 + j, t, v); };
     auto sink = [&](int j, const float (&o)[NF]) {
-      if (!active) return;
       const size_t idx = obase + (size_t)j * st;
       if (DIVIDE) {
         float qv = itk_divide(o[0], o[NF - 1]);
-        if (A.mask_u8) qv = __ldg(A.mask_u8 + idx) != 0 ? qv : 0.0f;
-        if (A.mask_f32) qv = __ldg(A.mask_f32 + idx) != 0.0f ? qv : 0.0f;
-        A.out0[idx] = qv;
-      } else {
+        if (active) {
+          if (MASKMODE == 1) qv = __ldg(A.mask_u8 + idx) != 0 ? qv : 0.0f;
+          if (MASKMODE == 2) qv = __ldg(A.mask_f32 + idx) != 0.0f ? qv : 0.0f;
+          A.out0[idx] = qv;
+        }
+      } else if (active) {
         A.out0[idx] = o[0];
         if (NF == 2) A.out1[idx] = o[NF - 1];
       }
