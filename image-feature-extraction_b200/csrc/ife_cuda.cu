@@ -169,8 +169,15 @@ constexpr int kAsyncStages = 3;
 
 template <int NF, int INMODE, bool DIVIDE, int MASKMODE, bool FMA>
 int launch_strided_async_m(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
-  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, MASKMODE, kChunk, FMA, kAsyncStages>;
-  const size_t smem = sizeof(AsyncStage<NF, INMODE, kChunk>) * kAsyncStages;
+  // Measured (512x512x400, two fields): the y pass (float fields, divide sink) is fastest with
+  // the replay buffer in shared memory, 2 stages and 3 CTAs/SM (0.91 vs 0.99 ms); the z pass
+  // (uint8 mask input) with the replay buffer in registers, 3 stages, 2 CTAs/SM (0.67 vs 0.71).
+  constexpr bool YBS = NF == 2 && INMODE == IN_FIELDS;
+  constexpr int STAGES = YBS ? 2 : kAsyncStages;
+  constexpr int MINB = YBS ? 3 : 1;
+  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, MASKMODE, kChunk, FMA, STAGES, YBS, MINB>;
+  const size_t smem = sizeof(AsyncStage<NF, INMODE, kChunk, !YBS>) * STAGES +
+                      (YBS ? (size_t)NF * kChunk * kAsyncThreads * sizeof(double) : 0);
   IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A.n_lines + kAsyncThreads - 1) / kAsyncThreads);
   kern<<<grid, kAsyncThreads, smem, ctx->stream()>>>(C, A);

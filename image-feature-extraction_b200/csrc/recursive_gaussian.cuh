@@ -143,11 +143,26 @@ __device__ __forceinline__ void forward_chunk(const GaussCoef& C, const SRC& src
   }
 }
 
-template <int NF, int L, bool FMA, bool GENERIC, typename SRC, typename SINK>
+// Where the replayed causal values of a chunk wait for the anticausal sweep: registers
+// (RegYB) or a per-thread column of shared memory (SmemYB), which frees 4*L registers per
+// thread and lets a third CTA fit on the SM.
+template <int NF, int L>
+struct RegYB {
+  double v[NF][L];
+  __device__ __forceinline__ void set(int f, int j, double x) { v[f][j] = x; }
+  __device__ __forceinline__ double get(int f, int j) const { return v[f][j]; }
+};
+template <int NF, int L, int THREADS>
+struct SmemYB {
+  double* col;  // this thread's column: element (f, j) at col[(f*L + j)*THREADS]
+  __device__ __forceinline__ void set(int f, int j, double x) { col[(f * L + j) * THREADS] = x; }
+  __device__ __forceinline__ double get(int f, int j) const { return col[(f * L + j) * THREADS]; }
+};
+
+template <int NF, int L, bool FMA, bool GENERIC, typename SRC, typename SINK, typename YB>
 __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& src, const SINK& sink,
                                                int i0, int len, int n, Rec (&cs)[NF],
-                                               Rec (&as)[NF]) {
-  double yb[NF][L];
+                                               Rec (&as)[NF], YB& yb) {
   {
     Fb fb = fb_select(C.D, C.BN, 4);
 #pragma unroll
@@ -157,7 +172,7 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& sr
         double v[NF];
         src(j, v);
 #pragma unroll
-        for (int f = 0; f < NF; ++f) yb[f][j] = causal_step<FMA>(C, fb, cs[f], v[f]);
+        for (int f = 0; f < NF; ++f) yb.set(f, j, causal_step<FMA>(C, fb, cs[f], v[f]));
       }
     }
   }
@@ -173,12 +188,20 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& sr
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const double w = anti_step<FMA>(C, fb, as[f], v[f]);
-          o[f] = (float)__dadd_rn(yb[f][j], w);
+          o[f] = (float)__dadd_rn(yb.get(f, j), w);
         }
         sink(j, o);
       }
     }
   }
+}
+
+template <int NF, int L, bool FMA, bool GENERIC, typename SRC, typename SINK>
+__device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& src, const SINK& sink,
+                                               int i0, int len, int n, Rec (&cs)[NF],
+                                               Rec (&as)[NF]) {
+  RegYB<NF, L> yb;
+  backward_chunk<NF, L, FMA, GENERIC>(C, src, sink, i0, len, n, cs, as, yb);
 }
 
 // chunk [i0, i0+len) of a line of n samples can take the hot path
@@ -394,17 +417,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int kAsyncThreads = 128;
 
-template <int NF, int INMODE, int L>
+template <int NF, int INMODE, int L, bool CK = true>
 struct AsyncStage {
   static constexpr int ROWS = L + 3;  // rows 0..2 = samples i0-3..i0-1, rows 3.. = the chunk
   float f0[ROWS][kAsyncThreads];
   // second field (float) or certainty (float / uint8, the latter packed in the first bytes)
   float f1[NF == 2 ? ROWS : 1][kAsyncThreads];
-  double ck[NF * 4][kAsyncThreads];
+  double ck[CK ? NF * 4 : 1][CK ? kAsyncThreads : 2];   // checkpoint slots (CK) or none
 };
 
-template <int NF, int INMODE, int L>
-__device__ __forceinline__ void stage_sample(const AsyncStage<NF, INMODE, L>& S, int row, int t,
+template <int NF, int INMODE, int L, bool CK>
+__device__ __forceinline__ void stage_sample(const AsyncStage<NF, INMODE, L, CK>& S, int row, int t,
                                              double (&v)[NF]) {
   if (INMODE == IN_FIELDS) {
     v[0] = (double)S.f0[row][t];
@@ -433,8 +456,8 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 // __syncwarp after cp.async.wait_group is all the synchronisation needed.
 // Host-checked: every warp's 32 lines are contiguous in memory (line stride 1, no wrap),
 // pointers and plane strides are 16-byte aligned, n_lines % 4 == 0 (% 16 with a uint8 mask).
-template <int NF, int INMODE, int L>
-__device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, INMODE, L>& S, int t,
+template <int NF, int INMODE, int L, bool CK>
+__device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, INMODE, L, CK>& S, int t,
                                             size_t wbase, long long wline, size_t line, bool active,
                                             int kc, int row_first, bool with_ckpt) {
   constexpr int ROWS = L + 3;
@@ -469,7 +492,7 @@ __device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, IN
                    reinterpret_cast<const uint8_t*>(A.in1) + wbase + (size_t)plane * st + 16 * h);
     }
   }
-  if (with_ckpt && kc >= 1 && active) {
+  if (CK && with_ckpt && kc >= 1 && active) {
     const double* src = A.ckpt + ckpt_index<NF>(kc, 0, 0, A.n_lines, line);
 #pragma unroll
     for (int k = 0; k < NF * 4; ++k) cp_async8(&S.ck[k][t], src + (size_t)k * (size_t)A.n_lines);
@@ -478,13 +501,18 @@ __device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, IN
 }
 
 // MASKMODE (DIVIDE only): 0 = no output mask, 1 = uint8 mask, 2 = float mask
-template <int NF, int INMODE, bool DIVIDE, int MASKMODE, int L, bool FMA, int STAGES>
-__global__ void __launch_bounds__(kAsyncThreads)
+// YBS: the replayed causal values live in shared memory and checkpoints are prefetched into
+// registers instead of stage slots; with STAGES = 2 that is 70 KB per CTA and < 170
+// registers per thread, so three CTAs (12 warps, 6 independent recurrences per SM
+// sub-partition) are resident instead of two.
+template <int NF, int INMODE, bool DIVIDE, int MASKMODE, int L, bool FMA, int STAGES, bool YBS, int MINB>
+__global__ void __launch_bounds__(kAsyncThreads, MINB)
 gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_constant__ PassArgs A) {
-  using Stage = AsyncStage<NF, INMODE, L>;
+  using Stage = AsyncStage<NF, INMODE, L, !YBS>;
   extern __shared__ __align__(16) unsigned char async_smem[];
   Stage* stages = reinterpret_cast<Stage*>(async_smem);
   const int t = threadIdx.x;
+  SmemYB<NF, L, kAsyncThreads> ybs{reinterpret_cast<double*>(async_smem + STAGES * sizeof(Stage)) + t};
   const long long line_ll = (long long)blockIdx.x * kAsyncThreads + t;
   const bool active = line_ll < A.n_lines;
   const size_t line = (size_t)(active ? line_ll : A.n_lines - 1);
@@ -503,12 +531,12 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   // ---- phase A: causal sweep, checkpoint at every chunk start ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < n_chunks) stage_issue<NF, INMODE, L>(A, stages[s], t, wbase, wline, line, active, s, 3, false);
+    if (s < n_chunks) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, s, 3, false);
     else cp_async_commit();
   }
   for (int k = 0; k < n_chunks; ++k) {
     const int kn = k + STAGES - 1;
-    if (kn < n_chunks) stage_issue<NF, INMODE, L>(A, stages[kn % STAGES], t, wbase, wline, line, active, kn, 3, false);
+    if (kn < n_chunks) stage_issue<NF, INMODE, L, !YBS>(A, stages[kn % STAGES], t, wbase, wline, line, active, kn, 3, false);
     else cp_async_commit();
     cp_async_wait<STAGES - 1>();
     __syncwarp();
@@ -517,7 +545,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     const int len = min(L, n - i0);
     if (k == 0) {
       double v[NF];
-      stage_sample<NF, INMODE, L>(S, 3, t, v);
+      stage_sample<NF, INMODE, L, !YBS>(S, 3, t, v);
 #pragma unroll
       for (int f = 0; f < NF; ++f) rec_fill(cs[f], v[f]);
     } else if (active) {
@@ -529,12 +557,12 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
         A.ckpt[ckpt_index<NF>(k, f, 3, A.n_lines, line)] = cs[f].h3;
       }
     }
-    auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L>(S, 3 + j, t, v); };
+    auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
     if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, src, i0, len, cs);
     else forward_chunk<NF, L, FMA, true>(C, src, i0, len, cs);
     if (k == n_chunks - 1) {  // the line's last sample is the anticausal edge value
       double v[NF];
-      stage_sample<NF, INMODE, L>(S, 3 + len - 1, t, v);
+      stage_sample<NF, INMODE, L, !YBS>(S, 3 + len - 1, t, v);
 #pragma unroll
       for (int f = 0; f < NF; ++f) rec_fill(as[f], v[f]);
     }
@@ -544,17 +572,25 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   __threadfence_block();
 
   // ---- phase B: backward over chunks, prefetching downwards ----
+  double ckn[NF][4];   // YBS: checkpoint of the chunk processed next, prefetched into registers
+  if (YBS) {
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ckn[f][k] = n_chunks >= 2 ? A.ckpt[ckpt_index<NF>(n_chunks - 1, f, k, A.n_lines, line)] : 0.0;
+  }
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     const int kc = n_chunks - 1 - s;
-    if (kc >= 0) stage_issue<NF, INMODE, L>(A, stages[s], t, wbase, wline, line, active, kc, 0, true);
+    if (kc >= 0) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, kc, 0, true);
     else cp_async_commit();
   }
   for (int q = 0; q < n_chunks; ++q) {
     const int k = n_chunks - 1 - q;
     const int qn = q + STAGES - 1;
     if (qn < n_chunks)
-      stage_issue<NF, INMODE, L>(A, stages[qn % STAGES], t, wbase, wline, line, active, n_chunks - 1 - qn, 0, true);
+      stage_issue<NF, INMODE, L, !YBS>(A, stages[qn % STAGES], t, wbase, wline, line, active, n_chunks - 1 - qn, 0, true);
     else cp_async_commit();
     cp_async_wait<STAGES - 1>();
     __syncwarp();
@@ -563,28 +599,38 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     const int len = min(L, n - i0);
     if (k == 0) {
       double v[NF];
-      stage_sample<NF, INMODE, L>(S, 3, t, v);
+      stage_sample<NF, INMODE, L, !YBS>(S, 3, t, v);
 #pragma unroll
       for (int f = 0; f < NF; ++f) rec_fill(cs[f], v[f]);
     } else {
       double v1[NF], v2[NF], v3[NF];
-      stage_sample<NF, INMODE, L>(S, 2, t, v1);
-      stage_sample<NF, INMODE, L>(S, 1, t, v2);
-      stage_sample<NF, INMODE, L>(S, 0, t, v3);
+      stage_sample<NF, INMODE, L, !YBS>(S, 2, t, v1);
+      stage_sample<NF, INMODE, L, !YBS>(S, 1, t, v2);
+      stage_sample<NF, INMODE, L, !YBS>(S, 0, t, v3);
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
-        cs[f].h0 = S.ck[f * 4 + 0][t];
-        cs[f].h1 = S.ck[f * 4 + 1][t];
-        cs[f].h2 = S.ck[f * 4 + 2][t];
-        cs[f].h3 = S.ck[f * 4 + 3][t];
+        if (YBS) {
+          cs[f].h0 = ckn[f][0]; cs[f].h1 = ckn[f][1]; cs[f].h2 = ckn[f][2]; cs[f].h3 = ckn[f][3];
+        } else {
+          cs[f].h0 = S.ck[f * 4 + 0][t];
+          cs[f].h1 = S.ck[f * 4 + 1][t];
+          cs[f].h2 = S.ck[f * 4 + 2][t];
+          cs[f].h3 = S.ck[f * 4 + 3][t];
+        }
         cs[f].x0 = v1[f];
         cs[f].x1 = v2[f];
         cs[f].x2 = v3[f];
         cs[f].x3 = 0.0;
       }
     }
+    if (YBS && k >= 2) {   // prefetch the next chunk's checkpoint; consumed one iteration later
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ckn[f][kk] = A.ckpt[ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)];
+    }
     const size_t obase = base + (size_t)i0 * st;
-    auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L>(S, 3 + j, t, v); };
+    auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
     auto sink = [&](int j, const float (&o)[NF]) {
       const size_t idx = obase + (size_t)j * st;
       if (DIVIDE) {
@@ -599,8 +645,13 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
         if (NF == 2) A.out1[idx] = o[NF - 1];
       }
     };
-    if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
-    else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
+    if (YBS) {
+      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as, ybs);
+      else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as, ybs);
+    } else {
+      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
+      else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
+    }
     __syncwarp();
   }
   cp_async_wait<0>();
