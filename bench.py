@@ -185,6 +185,95 @@ def cpu_baseline(torch, img_dev, mask_dev):
                       (DIMS[0], DIMS[1], CPU_SAMPLE_NZ, len(SIGMAS), dt)}
 
 
+def run_slab(args, torch, dist, ctx, stream, dev, world, rank, local_rank, warmup, out_stream):
+    """BASELINE.json configs[3]: ONE size^3 volume cut into z-slabs over the ranks; halo
+    exchange with ncclSend/ncclRecv inside ife_cuda_slab_emphysema_features (strong scaling)."""
+    import ife_b200
+    size = args.slab_size
+    gd = (size, size, size)
+    z0, z1 = ife_b200.slab_range(size, world, rank)
+    nzo = z1 - z0
+    plane = size * size
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    coarse = torch.randn((1, 1, size // 16 + 1, size // 16 + 1, size // 16 + 1), generator=g, device=dev)
+    # every rank builds only its own planes of the same global volume
+    zs = torch.linspace(-1, 1, size, device=dev)[z0:z1]
+    ys = torch.linspace(-1, 1, size, device=dev)
+    grid = torch.stack(torch.meshgrid(zs, ys, ys, indexing="ij")[::-1], dim=-1)[None]
+    img = torch.nn.functional.grid_sample(coarse, grid, mode="bilinear", align_corners=True)[0, 0]
+    del grid
+    img = (img * 300.0 - 800.0 + 30.0 * torch.randn(img.shape, generator=g, device=dev)).contiguous()
+    mask = torch.ones((nzo, size, size), dtype=torch.uint8, device=dev)
+    n_own = nzo * plane
+    per_scale = 8 * n_own * 4 > 40e9          # one scale's outputs at a time when they would not fit
+    out = torch.empty(((1 if per_scale else len(SIGMAS)), 8, nzo, size, size), dtype=torch.float32, device=dev)
+    if world > 1:
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], world, rank)
+    torch.cuda.synchronize()
+
+    def step():
+        if per_scale:
+            for s in SIGMAS:
+                ctx.slab_emphysema_features_dev(img.data_ptr(), mask.data_ptr(), out.data_ptr(), gd, [s])
+        else:
+            ctx.slab_emphysema_features_dev(img.data_ptr(), mask.data_ptr(), out.data_ptr(), gd, SIGMAS)
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()          # before the barrier: its start-up must not skew the ranks
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    units = size ** 3 * len(SIGMAS)
+    ms_per_step = ms / args.steps
+    value = units / (ms_per_step * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    halo = ife_b200.slab_halo(max(SIGMAS))
+    if rank == 0:
+        out_stream.emit(json.dumps({
+            "metric": METRIC.replace("512^2x400 CT", "%d^3 volume, z-slabs" % size), "value": value, "unit": "Gvoxel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 recursion / f32 stencil+solver", "data": "synthetic",
+            "config": {"workload": "one %d^3 float volume cut into %d z-slabs, sigma{0.6,1.2,2.4,4.8}, 8 masked feature "
+                                   "volumes per scale, NCCL halo exchange (%d planes per side at the largest scale, default "
+                                   "halo factor 12)" % (size, world, halo), "mask": "ones", "arith": args.arith,
+                       "outputs": "one scale at a time" if per_scale else "all scales resident"},
+            "roofline": {"bound": "hbm", "kernel": "pipeline", "achieved": 78 * units / (ms_per_step * 1e-3) / 1e9 / world,
+                         "peak": peak, "unit": "GB/s", "frac": 78 * units / (ms_per_step * 1e-3) / 1e9 / world / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "per-GPU algorithmic bytes (78 B/voxel-scale) over the step time"},
+            "e2e": None, "cpu_baseline": None, "gpu_launches": launches, "clocks": clocks,
+        }))
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
 class QuietStdout:
     """Routes fd 1 to stderr while the benchmark runs (NCCL and friends print banners on
     stdout) so that the JSON line is the ONLY thing this process writes to stdout."""
@@ -222,6 +311,7 @@ def _main(out_stream):
     ap.add_argument("--workload", default="extract", choices=["extract", "hist", "slab"])
     ap.add_argument("--mask", default="ones", choices=["ones", "lung"])
     ap.add_argument("--arith", default="fma", choices=["fma", "plain"])
+    ap.add_argument("--slab-size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -246,11 +336,13 @@ def _main(out_stream):
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
 
-    nx, ny, nz = DIMS
-    n = nx * ny * nz
     ctx = ife_b200.Context(local_rank, arith=ife_b200.ARITH_FMA if args.arith == "fma" else ife_b200.ARITH_PLAIN)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
+    if args.workload == "slab":
+        return run_slab(args, torch, dist, ctx, stream, dev, world, rank, local_rank, warmup, out_stream)
+    nx, ny, nz = DIMS
+    n = nx * ny * nz
     img, mask = synth_scan_torch(torch, dev, 100 + rank, args.mask)
     hist = args.workload == "hist"
     edges = None
@@ -274,12 +366,12 @@ def _main(out_stream):
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()          # before the barrier: its start-up must not skew the ranks
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         ctx.profile_enable(True)
         l0 = ctx.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
