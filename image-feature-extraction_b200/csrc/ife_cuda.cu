@@ -281,6 +281,7 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   // z pass: lines = nx*ny columns, contiguous across the plane
   A.in0 = in0; A.in1 = cert; A.out0 = a0; A.out1 = a1;
   A.n = nzb; A.stride = (long long)nx * ny; A.na = nx * ny > 0 ? nx * ny : 1; A.sb = 0;
+  A.out_lo = keep0; A.out_hi = keep1;   // a z-slab's halo planes only carry recursion state
   A.n_lines = (long long)nx * ny;
   if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cz, A)));
   else if (cert_is_u8) IFE_TRY((launch_strided<2, IN_IMG_U8, false>(ctx, cz, A)));
@@ -291,12 +292,14 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   const size_t koff = (size_t)keep0 * nx * ny;
   A.in0 = a0 + koff; A.in1 = a1 + koff; A.out0 = b0; A.out1 = b1;
   A.n = nx; A.stride = 1; A.na = 1; A.sb = 0; A.n_lines = (long long)ny * nzk;
+  A.out_lo = 0; A.out_hi = nx;
   if (nf == 1) IFE_TRY((launch_x<1>(ctx, cx, A)));
   else IFE_TRY((launch_x<2>(ctx, cx, A)));
 
   // y pass: lines indexed (x, z); base = x + z*nx*ny; stride nx
   A.in0 = b0; A.in1 = b1; A.out0 = out0; A.out1 = nullptr;
   A.n = ny; A.stride = nx; A.na = nx; A.sb = (long long)nx * ny; A.n_lines = (long long)nx * nzk;
+  A.out_lo = 0; A.out_hi = ny;
   A.mask_u8 = outmask_u8; A.mask_f32 = outmask_f32;
   if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cy, A)));
   else IFE_TRY((launch_strided<2, IN_FIELDS, true>(ctx, cy, A)));

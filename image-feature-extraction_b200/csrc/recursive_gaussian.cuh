@@ -204,6 +204,24 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& sr
   backward_chunk<NF, L, FMA, GENERIC>(C, src, sink, i0, len, n, cs, as, yb);
 }
 
+// anticausal recurrence only (no output): used above the wanted output range, where a
+// z-slab's warm-up halo only has to deliver the recursion state at the slab's upper edge
+template <int NF, int L, bool FMA, bool GENERIC, typename SRC>
+__device__ __forceinline__ void anti_chunk(const GaussCoef& C, const SRC& src, int i0, int len, int n,
+                                           Rec (&as)[NF]) {
+  Fb fb = fb_select(C.D, C.BM, 4);
+#pragma unroll
+  for (int j = L - 1; j >= 0; --j) {
+    if (!GENERIC || j < len) {
+      if (GENERIC) fb = fb_select(C.D, C.BM, n - 1 - (i0 + j));
+      double v[NF];
+      src(j, v);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) anti_step<FMA>(C, fb, as[f], v[f]);
+    }
+  }
+}
+
 // chunk [i0, i0+len) of a line of n samples can take the hot path
 template <int L>
 __device__ __forceinline__ bool chunk_is_interior(int i0, int len, int n) {
@@ -251,6 +269,8 @@ struct PassArgs {
   const float* mask_f32;    //   "
   double* ckpt;
   int n;                // samples per line
+  int out_lo, out_hi;   // samples [out_lo, out_hi) of every line are wanted (z-slabs: the rest
+                        // is warm-up halo); outside it only the recursion state is advanced
   long long stride;     // element stride between consecutive samples of a line
   int na;               // lines are indexed l = a + na*b, base = a + b*sb  (strided pass)
   long long sb;
@@ -528,15 +548,20 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   Rec cs[NF];
   Rec as[NF];
 
+  // chunks [0, kA) need the causal sweep (nothing above the output range does); chunks
+  // [k_lo, n_chunks) the anticausal one; only chunks in [k_lo, kA) produce output
+  const int kA = min(n_chunks, (A.out_hi + L - 1) / L);
+  const int k_lo = max(0, A.out_lo) / L;
+
   // ---- phase A: causal sweep, checkpoint at every chunk start ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < n_chunks) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, s, 3, false);
+    if (s < kA) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, s, 3, false);
     else cp_async_commit();
   }
-  for (int k = 0; k < n_chunks; ++k) {
+  for (int k = 0; k < kA; ++k) {
     const int kn = k + STAGES - 1;
-    if (kn < n_chunks) stage_issue<NF, INMODE, L, !YBS>(A, stages[kn % STAGES], t, wbase, wline, line, active, kn, 3, false);
+    if (kn < kA) stage_issue<NF, INMODE, L, !YBS>(A, stages[kn % STAGES], t, wbase, wline, line, active, kn, 3, false);
     else cp_async_commit();
     cp_async_wait<STAGES - 1>();
     __syncwarp();
@@ -570,6 +595,12 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   }
   cp_async_wait<0>();
   __threadfence_block();
+  if (kA < n_chunks) {  // phase A stopped early: fetch the edge value directly
+    float v[NF];
+    load_sample<NF, INMODE>(A, base + (size_t)(n - 1) * st, v);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) rec_fill(as[f], (double)v[f]);
+  }
 
   // ---- phase B: backward over chunks, prefetching downwards ----
   double ckn[NF][4];   // YBS: checkpoint of the chunk processed next, prefetched into registers
@@ -578,25 +609,42 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     for (int f = 0; f < NF; ++f)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        ckn[f][k] = n_chunks >= 2 ? A.ckpt[ckpt_index<NF>(n_chunks - 1, f, k, A.n_lines, line)] : 0.0;
+        ckn[f][k] = (kA == n_chunks && n_chunks >= 2) ? A.ckpt[ckpt_index<NF>(n_chunks - 1, f, k, A.n_lines, line)] : 0.0;
   }
+  const int nB = n_chunks - k_lo;   // chunks n_chunks-1 .. k_lo
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     const int kc = n_chunks - 1 - s;
-    if (kc >= 0) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, kc, 0, true);
+    if (s < nB) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, kc, kc < kA ? 0 : 3, kc < kA);
     else cp_async_commit();
   }
-  for (int q = 0; q < n_chunks; ++q) {
+  for (int q = 0; q < nB; ++q) {
     const int k = n_chunks - 1 - q;
     const int qn = q + STAGES - 1;
-    if (qn < n_chunks)
-      stage_issue<NF, INMODE, L, !YBS>(A, stages[qn % STAGES], t, wbase, wline, line, active, n_chunks - 1 - qn, 0, true);
-    else cp_async_commit();
+    if (qn < nB) {
+      const int kc = n_chunks - 1 - qn;
+      stage_issue<NF, INMODE, L, !YBS>(A, stages[qn % STAGES], t, wbase, wline, line, active, kc, kc < kA ? 0 : 3, kc < kA);
+    } else {
+      cp_async_commit();
+    }
     cp_async_wait<STAGES - 1>();
     __syncwarp();
     const Stage& S = stages[q % STAGES];
     const int i0 = k * L;
     const int len = min(L, n - i0);
+    if (k >= kA) {   // above the output range: only the anticausal state moves
+      auto srca = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
+      if (chunk_is_interior<L>(i0, len, n)) anti_chunk<NF, L, FMA, false>(C, srca, i0, len, n, as);
+      else anti_chunk<NF, L, FMA, true>(C, srca, i0, len, n, as);
+      if (YBS && k - 1 >= 1 && k - 1 < kA) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) ckn[f][kk] = A.ckpt[ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)];
+      }
+      __syncwarp();
+      continue;
+    }
     if (k == 0) {
       double v[NF];
       stage_sample<NF, INMODE, L, !YBS>(S, 3, t, v);
