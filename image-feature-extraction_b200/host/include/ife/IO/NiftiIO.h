@@ -126,6 +126,7 @@ template <typename T> struct DataType;
 template <> struct DataType<float> { static const int16_t code = DT_FLOAT32; };
 template <> struct DataType<unsigned char> { static const int16_t code = DT_UINT8; };
 template <> struct DataType<short> { static const int16_t code = DT_INT16; };
+template <> struct DataType<unsigned short> { static const int16_t code = DT_UINT16; };
 
 template <typename T>
 void Write(const std::string& path, const Geometry& g, const T* data) {

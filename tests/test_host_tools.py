@@ -25,7 +25,8 @@ def test_host_selftest(tmp_path):
 @pytest.mark.parametrize("tool,required", [("ExtractFeatures", "-i -m -o -s"),
                                            ("MaskedNormalizedConvolution", "-i -c -s -o"),
                                            ("FiniteDifference_HessianFeatures", "-i -m -o"),
-                                           ("FiniteDifference_GradientFeatures", "-i -m -o")])
+                                           ("FiniteDifference_GradientFeatures", "-i -m -o"),
+                                           ("MakeBag", "-i -m -H -o -s")])
 def test_cli_surface(tool, required):
     p = run(tool, "--help")
     assert p.returncode == 0
@@ -89,3 +90,49 @@ def test_tools_end_to_end_against_oracle(tmp_path, oracle):
     assert p.returncode == 0, p.stderr
     got, _ = nifti_util.read(d + "/gradient_GradientMagnitude.nii.gz")
     assert np.array_equal(got, oracle.fd_gradient_features(imgf, lab.astype(np.float32), spacing=sp))
+
+
+@pytest.mark.gpu
+def test_makebag_against_oracle(tmp_path, oracle):
+    """tools/MakeBag.cxx semantics: ROI file in, one CSV row of 8*|scales| histograms'
+    frequencies per ROI out; and the random-ROI mode writes a .ROIInfo that reads back."""
+    shape = (30, 34, 38)
+    img = synth.ct_like(shape, seed=61, n_blobs=8)
+    lab = synth.lung_mask(shape).astype(np.uint16)
+    m01 = synth.clamp01(lab.astype(np.uint8))
+    d = str(tmp_path)
+    nifti_util.write(d + "/img.nii.gz", img)
+    nifti_util.write(d + "/mask.nii.gz", lab)
+    sigmas = [0.6, 1.2]
+    feats = np.concatenate([oracle.emphysema_features(img, m01, float(np.float32(s)), arith=1) for s in sigmas])
+    edges = np.stack([synth.equalized_edges(feats[k][m01 != 0], 10) for k in range(16)])
+    with open(d + "/hist.txt", "w") as f:
+        f.write("# one row per (scale, feature)\n")
+        for row in edges:
+            f.write(",".join(repr(float(v)) for v in row) + "\n")
+    rois = synth.random_rois(m01, 5, (9, 7, 5), seed=4)
+    with open(d + "/rois.txt", "w") as f:
+        f.write("header line\n")
+        for r in rois:
+            f.write("[%d, %d, %d][%d, %d, %d]\n" % tuple(r))
+    p = run("MakeBag", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d,
+            "-s", "0.6", "-s", "1.2", "-r", d + "/rois.txt", "-p", "case")
+    assert p.returncode == 0, p.stderr
+    assert "Got 5 rois." in p.stdout and "Skipping a line" in p.stdout
+    bag = np.loadtxt(d + "/case.bag", delimiter=",", ndmin=2)
+    assert bag.shape == (5, 16 * 11)
+    counts = oracle.features_histograms(feats, m01, edges, rois).astype(np.float32)    # (5, 16, 11)
+    freq = counts / counts.sum(2, keepdims=True)
+    assert np.allclose(bag.reshape(5, 16, 11), freq, rtol=2e-5, atol=1e-7, equal_nan=True)
+    assert np.allclose(np.nansum(bag.reshape(5, 16, 11), axis=2), 1.0, atol=1e-4)
+    # random ROI mode
+    p = run("MakeBag", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d,
+            "-s", "0.6", "-s", "1.2", "-n", "7", "-x", "9", "-y", "7", "-z", "5", "-p", "rnd", "-S", "3")
+    assert p.returncode == 0, p.stderr
+    lines = open(d + "/rnd.ROIInfo").read().strip().splitlines()
+    assert len(lines) == 7 and all(l.endswith("[9, 7, 5]") for l in lines)
+    assert np.loadtxt(d + "/rnd.bag", delimiter=",", ndmin=2).shape == (7, 16 * 11)
+    # wrong number of histogram rows -> the reference's error and exit code
+    p = run("MakeBag", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d, "-s", "0.6",
+            "-r", d + "/rois.txt")
+    assert p.returncode == 1 and "Number of histograms must match" in p.stderr
