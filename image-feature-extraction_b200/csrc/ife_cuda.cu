@@ -172,7 +172,7 @@ int launch_strided_async_m(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs
   // Measured (512x512x400, two fields): the y pass (float fields, divide sink) is fastest with
   // the replay buffer in shared memory, 2 stages and 3 CTAs/SM (0.91 vs 0.99 ms); the z pass
   // (uint8 mask input) with the replay buffer in registers, 3 stages, 2 CTAs/SM (0.67 vs 0.71).
-  constexpr bool YBS = NF == 2 && INMODE == IN_FIELDS;
+  constexpr bool YBS = NF == 2;
   constexpr int STAGES = YBS ? 2 : kAsyncStages;
   constexpr int MINB = YBS ? 3 : 1;
   auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, MASKMODE, kChunk, FMA, STAGES, YBS, MINB>;

@@ -127,11 +127,11 @@ __device__ __forceinline__ size_t ckpt_index(int chunk, int f, int k, size_t n_l
 // the recurrence.  GENERIC = true handles the first chunk (boundary coefficients), the
 // last chunk(s) and partial chunks.
 // ---------------------------------------------------------------------------------------
-template <int NF, int L, bool FMA, bool GENERIC, typename SRC>
+template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, typename SRC>
 __device__ __forceinline__ void forward_chunk(const GaussCoef& C, const SRC& src, int i0, int len,
                                               Rec (&cs)[NF]) {
   Fb fb = fb_select(C.D, C.BN, 4);
-#pragma unroll
+#pragma unroll UNROLL
   for (int j = 0; j < L; ++j) {
     if (!GENERIC || j < len) {
       if (GENERIC) fb = fb_select(C.D, C.BN, i0 + j);
@@ -159,13 +159,13 @@ struct SmemYB {
   __device__ __forceinline__ double get(int f, int j) const { return col[(f * L + j) * THREADS]; }
 };
 
-template <int NF, int L, bool FMA, bool GENERIC, typename SRC, typename SINK, typename YB>
+template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, typename SRC, typename SINK, typename YB>
 __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& src, const SINK& sink,
                                                int i0, int len, int n, Rec (&cs)[NF],
                                                Rec (&as)[NF], YB& yb) {
   {
     Fb fb = fb_select(C.D, C.BN, 4);
-#pragma unroll
+#pragma unroll UNROLL
     for (int j = 0; j < L; ++j) {
       if (!GENERIC || j < len) {
         if (GENERIC) fb = fb_select(C.D, C.BN, i0 + j);
@@ -178,7 +178,7 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& sr
   }
   {
     Fb fb = fb_select(C.D, C.BM, 4);
-#pragma unroll
+#pragma unroll UNROLL
     for (int j = L - 1; j >= 0; --j) {
       if (!GENERIC || j < len) {
         if (GENERIC) fb = fb_select(C.D, C.BM, n - 1 - (i0 + j));
@@ -201,7 +201,7 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& sr
                                                int i0, int len, int n, Rec (&cs)[NF],
                                                Rec (&as)[NF]) {
   RegYB<NF, L> yb;
-  backward_chunk<NF, L, FMA, GENERIC>(C, src, sink, i0, len, n, cs, as, yb);
+  backward_chunk<NF, L, FMA, GENERIC, L>(C, src, sink, i0, len, n, cs, as, yb);
 }
 
 // anticausal recurrence only (no output): used above the wanted output range, where a
@@ -436,6 +436,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kAsyncThreads = 128;
+constexpr int kYbsUnroll = 4;
 
 template <int NF, int INMODE, int L, bool CK = true>
 struct AsyncStage {
@@ -583,8 +584,8 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
       }
     }
     auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
-    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false>(C, src, i0, len, cs);
-    else forward_chunk<NF, L, FMA, true>(C, src, i0, len, cs);
+    if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false, YBS ? kYbsUnroll : L>(C, src, i0, len, cs);
+    else forward_chunk<NF, L, FMA, true, YBS ? 1 : L>(C, src, i0, len, cs);
     if (k == n_chunks - 1) {  // the line's last sample is the anticausal edge value
       double v[NF];
       stage_sample<NF, INMODE, L, !YBS>(S, 3 + len - 1, t, v);
@@ -694,8 +695,10 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
       }
     };
     if (YBS) {
-      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as, ybs);
-      else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as, ybs);
+      // samples and replay buffer are both in shared memory: the loops need no register arrays
+      // and can stay partially rolled (smaller code, fewer instruction-cache misses)
+      if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false, kYbsUnroll>(C, src, sink, i0, len, n, cs, as, ybs);
+      else backward_chunk<NF, L, FMA, true, 1>(C, src, sink, i0, len, n, cs, as, ybs);
     } else {
       if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
       else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
