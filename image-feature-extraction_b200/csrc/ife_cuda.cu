@@ -325,8 +325,12 @@ int reserve_smoothing(ife_cuda_ctx* ctx, int nf, int nx, int ny, int nzb) {
 template <int MODE, bool HIST>
 void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                        const StencilCoef& S, const FeatArgs& A) {
-  if (unit) features_kernel<MODE, HIST, true><<<grid, block, smem, st>>>(S, A);
-  else features_kernel<MODE, HIST, false><<<grid, block, smem, st>>>(S, A);
+  constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
+  bool all = true;
+  for (int k = 0; k < NFEAT; ++k) all = all && A.out[k] != nullptr;
+  if (all && unit) features_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A);
+  else if (unit) features_kernel<MODE, HIST, true, false><<<grid, block, smem, st>>>(S, A);
+  else features_kernel<MODE, HIST, false, false><<<grid, block, smem, st>>>(S, A);
 }
 
 int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const FeatArgs& A,

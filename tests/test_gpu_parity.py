@@ -4,9 +4,10 @@ CPU oracle on the same seeded inputs.
 Bar (BASELINE.json north_star): eigenvalues within 1e-4 * max|lambda| per voxel with the
 same ordering; histogram counts exact except for voxels within that tolerance of an edge.
 What is asserted here is stronger: every stage is BIT-IDENTICAL to the oracle run in the
-same arithmetic mode, except that the solver's double-precision acos/cos come from CUDA's
-libdevice instead of glibc, which after narrowing to float may flip the last bit of an
-eigenvalue for a vanishing fraction of voxels (<= MISMATCH_FRAC, each still within TOL).
+same arithmetic mode, except that the solver's double-precision acos/cos are polynomial
+kernels within ~1 ulp of glibc's instead of glibc itself, which after narrowing to float may
+flip the last bit of an eigenvalue for a vanishing fraction of voxels (<= MISMATCH_FRAC,
+each still within TOL; currently none is observed).
 """
 import numpy as np
 import pytest
@@ -16,7 +17,7 @@ import synth
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4            # relative to max|lambda| per voxel (north_star)
-MISMATCH_FRAC = 2e-5  # allowed fraction of last-bit differences from libm vs libdevice
+MISMATCH_FRAC = 2e-5  # allowed fraction of last-bit differences (libm vs the polynomial acos/cos)
 
 
 def bits_equal(a, b):
