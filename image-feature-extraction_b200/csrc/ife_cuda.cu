@@ -12,6 +12,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "eigen_features.cuh"
 #include "recursive_gaussian.cuh"
@@ -793,6 +794,30 @@ int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const f
                                       cudaMemcpyDeviceToHost, ctx->stream()));
     IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
   }
+  return IFE_OK;
+}
+
+int ife_cuda_sort_f32(ife_cuda_ctx* ctx, float* data, size_t n, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (n == 0) return IFE_OK;
+  if (!data) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  if (n > (size_t)0x7fffffff) return fail(ctx, IFE_E_INVALID, "too many samples for one sort (%zu)", n);
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const float* d_in_c;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, (const float*)data, n, mem, &d_in_c));
+  float* d_in = const_cast<float*>(d_in_c);
+  IFE_TRY(ctx->ws.out[0].reserve(ctx, n * sizeof(float)));
+  float* d_alt = (float*)ctx->ws.out[0].ptr;
+  cub::DoubleBuffer<float> keys(d_in, d_alt);
+  size_t tmp_bytes = 0;
+  IFE_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (int)n, 0, 32, ctx->stream()));
+  IFE_TRY(ctx->ws.blur.reserve(ctx, tmp_bytes));
+  IFE_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(ctx->ws.blur.ptr, tmp_bytes, keys, (int)n, 0, 32, ctx->stream()));
+  ctx->launches++;
+  const cudaMemcpyKind kind = mem == IFE_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (mem == IFE_MEM_HOST || keys.Current() != data)
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(data, keys.Current(), n * sizeof(float), kind, ctx->stream()));
+  if (mem == IFE_MEM_HOST) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
   return IFE_OK;
 }
 

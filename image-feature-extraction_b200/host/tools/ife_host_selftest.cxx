@@ -2,8 +2,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <sstream>
+
+#include <vector>
 
 #include "ife/IO/NiftiIO.h"
+#include "ife/IO/ROIReader.h"
+#include "ife/Statistics/DetermineEdgesForEqualizedHistogram.h"
 #include "ife/Util/CmdLine.h"
 #include "ife/Util/Path.h"
 
@@ -25,6 +30,28 @@ int main(int argc, char* argv[]) {
     float f;
     CHECK(ife::CmdLine::convert(cmd.values("scale")[2], &f) && f == 2.4f);
     CHECK(std::to_string(0.6f) == "0.600000");
+  }
+  {  // test/DetermineEdgesForEqualizedHistogramTest.cxx:30-70
+    std::vector<double> v{1, 2, 3, 4, 5, 6, 7, 8, 9}, e(2);
+    ife::determineEdgesForEqualizedHistogram(v.begin(), v.end(), e.begin(), 3);
+    CHECK(e[0] == 4 && e[1] == 7);
+    std::vector<double> ones(8, 1), e1{0, 123};
+    ife::determineEdgesForEqualizedHistogram(ones.begin(), ones.end(), e1.begin(), 2);
+    CHECK(e1[0] == 1);
+    std::vector<double> u{1, 1, 1, 1, 1, 2, 2, 3, 3, 3};
+    ife::determineEdgesForEqualizedHistogram(u.begin(), u.end(), e.begin(), 3);
+    CHECK(e[0] == 2 && e[1] == 3);
+    bool threw = false;
+    std::vector<double> e9(9);
+    try { ife::determineEdgesForEqualizedHistogram(v.begin(), v.end(), e9.begin(), 10); } catch (const std::out_of_range&) { threw = true; }
+    CHECK(threw);
+  }
+  {  // ROI text format round trip
+    std::stringstream ss;
+    ife::ROIReader::write(ss, {ife::Region{{1, 2, 3, 41, 41, 41}}, ife::Region{{0, 0, 7, 5, 6, 7}}});
+    CHECK(ss.str() == "[1, 2, 3][41, 41, 41]\n[0, 0, 7][5, 6, 7]\n");
+    auto back = ife::ROIReader::read(ss, false);
+    CHECK(back.size() == 2 && back[1][2] == 7 && back[0][5] == 41);
   }
   const std::string dir = argc > 1 ? argv[1] : "/tmp";
   auto img = ife::Image<float>::New();

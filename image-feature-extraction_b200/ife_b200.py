@@ -71,6 +71,7 @@ def load_library():
     L.ife_cuda_emphysema_histograms.argtypes = [vp, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp, i]
     L.ife_cuda_histogram.argtypes = [vp, vp, sz, vp, i, vp, i]
     L.ife_cuda_eigen_features_batch.argtypes = [vp, vp, vp, sz, i]
+    L.ife_cuda_sort_f32.argtypes = [vp, vp, sz, i]
     L.ife_cuda_comm_unique_id.argtypes = [vp, vp]
     L.ife_cuda_comm_init.argtypes = [vp, vp, i, i]
     L.ife_cuda_comm_destroy.argtypes = [vp]
@@ -265,6 +266,11 @@ class Context:
                                               values.size, _ptr(edges), edges.size, _ptr(counts),
                                               MEM_HOST))
         return counts
+
+    def sort(self, values):
+        v = np.array(values, np.float32).ravel()
+        self._check(self.L.ife_cuda_sort_f32(self.h, _ptr(v) if v.size else None, v.size, MEM_HOST))
+        return v
 
     def eigen_features_batch(self, A6):
         A6 = np.ascontiguousarray(A6, np.float32).reshape(-1, 6)

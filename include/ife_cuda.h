@@ -168,6 +168,12 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
 int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const float* edges,
                        int n_edges, uint32_t* counts, int mem);
 
+/* Ascending in-place sort of n floats: the `std::sort` of the feature samples in
+ * tools/DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx:282-283 (device radix
+ * sort; the equal-frequency edge walk of DetermineEdgesForEqualizedHistogram.h then runs
+ * on the host, it touches O(bins * log n) samples). */
+int ife_cuda_sort_f32(ife_cuda_ctx* ctx, float* data, size_t n, int mem);
+
 /* EigenvalueFeaturesFunctor<float> (and through it Symmetric3x3EigenvalueSolver<float>,
  * include/ife/Numerics/Symmetric3x3EigenvalueSolver.h:33-132) over n interleaved
  * matrices A6 = [A11,A12,A13,A22,A23,A33]; out6 interleaved. */

@@ -26,7 +26,8 @@ def test_host_selftest(tmp_path):
                                            ("MaskedNormalizedConvolution", "-i -c -s -o"),
                                            ("FiniteDifference_HessianFeatures", "-i -m -o"),
                                            ("FiniteDifference_GradientFeatures", "-i -m -o"),
-                                           ("MakeBag", "-i -m -H -o -s")])
+                                           ("MakeBag", "-i -m -H -o -s"),
+                                           ("DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures", "-i -o -b -S -s -f")])
 def test_cli_surface(tool, required):
     p = run(tool, "--help")
     assert p.returncode == 0
@@ -136,3 +137,41 @@ def test_makebag_against_oracle(tmp_path, oracle):
     p = run("MakeBag", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d, "-s", "0.6",
             "-r", d + "/rois.txt")
     assert p.returncode == 1 and "Number of histograms must match" in p.stderr
+
+
+@pytest.mark.gpu
+def test_determine_bin_edges_tool_against_oracle(tmp_path, oracle, ctx):
+    """tools/DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx with -S 0 (all
+    foreground voxels of two scans): edges == the reference's edge walk on the sorted oracle
+    features; the output feeds MakeBag unchanged."""
+    d = str(tmp_path)
+    shapes = [(20, 24, 28), (18, 26, 22)]
+    per_row = [[] for _ in range(16)]
+    with open(d + "/pairs.txt", "w") as f:
+        for i, shape in enumerate(shapes):
+            img = synth.ct_like(shape, seed=70 + i, n_blobs=6)
+            lab = synth.lung_mask(shape).astype(np.uint16)
+            nifti_util.write("%s/img%d.nii.gz" % (d, i), img)
+            nifti_util.write("%s/mask%d.nii.gz" % (d, i), lab)
+            f.write("%s/img%d.nii.gz, %s/mask%d.nii.gz\n\n" % (d, i, d, i))
+            m01 = synth.clamp01(lab.astype(np.uint8))
+            for s, sigma in enumerate((0.6, 1.2)):
+                feats = oracle.emphysema_features(img, m01, float(np.float32(sigma)), arith=1)
+                for k in range(8):
+                    per_row[s * 8 + k].append(feats[k][lab == 2])        # foreground value 2 only
+    p = run("DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures", "-i", d + "/pairs.txt", "-o", d + "/edges.txt",
+            "-b", "11", "-S", "0", "-s", "0.6", "-s", "1.2", "-f", "2")
+    assert p.returncode == 0, p.stderr
+    lines = open(d + "/edges.txt").read().splitlines()
+    assert lines[0].startswith("# Features: GaussianBlur") and lines[1] == "# Scales: 0.6 1.2"
+    rows = [np.array([float(v) for v in l.split(",")]) for l in lines[2:]]
+    assert len(rows) == 16 and all(len(r) == 10 for r in rows)
+    for r, parts in zip(rows, per_row):
+        s = np.sort(np.concatenate(parts).astype(np.float32))
+        ref = oracle.determine_edges(s, 11, dtype=np.float32)
+        assert np.allclose(r, ref, rtol=2e-5, atol=1e-12)
+    # the device sort on its own, incl. duplicates, negative zero and infinities
+    v = np.concatenate([np.random.default_rng(0).standard_normal(100001).astype(np.float32),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1.0, 1.0], np.float32)])
+    assert np.array_equal(ctx.sort(v), np.sort(v))
+    assert ctx.sort(np.zeros(0, np.float32)).size == 0
