@@ -167,22 +167,41 @@ def run_reference(args, out_stream):
     }))
 
 
-def cpu_baseline(torch, img_dev, mask_dev):
+def cpu_baseline(torch, img_dev, mask_dev, ctx, arith):
+    """Times the CPU oracle on a bounded sample and, with the oracle's output in hand, reports
+    the parity of the CUDA path on that same sample (SURVEY.md section 8d parity metrics)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
     import oracle as O
     O.build()
     cores = os.cpu_count() or 1
     img = img_dev[:CPU_SAMPLE_NZ].cpu().numpy()
     mask = mask_dev[:CPU_SAMPLE_NZ].cpu().numpy()
+    oarith = O.ARITH_FMA if arith == "fma" else O.ARITH_PLAIN
+    ref = []
     t0 = time.perf_counter()
     for s in SIGMAS:
-        O.emphysema_features_reference_arm(img, mask, s, arith=O.ARITH_PLAIN, threads=cores)
+        ref.append(O.emphysema_features_reference_arm(img, mask, s, arith=oarith, threads=cores))
     dt = time.perf_counter() - t0
+    ref = np.stack(ref)
+    gpu = ctx.emphysema_features(img, mask, SIGMAS)
+    same = (gpu == ref) | (np.isnan(gpu) & np.isnan(ref))
+    lam_ref, lam_gpu = ref[:, 2:5], gpu[:, 2:5]
+    scale = np.abs(lam_ref).max(1)
+    err = np.abs(lam_gpu.astype(np.float64) - lam_ref).max(1)
+    rel = np.where(scale > 0, err / np.where(scale > 0, scale, 1), 0.0)
+    order_ok = (np.abs(lam_gpu[:, 0]) >= np.abs(lam_gpu[:, 1])) & (np.abs(lam_gpu[:, 1]) >= np.abs(lam_gpu[:, 2]))
+    order_ref = (np.abs(lam_ref[:, 0]) >= np.abs(lam_ref[:, 1])) & (np.abs(lam_ref[:, 1]) >= np.abs(lam_ref[:, 2]))
+    parity = {"sample_voxel_scales": int(img.size * len(SIGMAS)), "values_compared": int(ref.size),
+              "values_differing": int((~same).sum()), "eig_max_rel_err": float(rel.max()),
+              "eig_p99_rel_err": float(np.percentile(rel, 99)), "eig_frac_gt_1e-4": float((rel > 1e-4).mean()),
+              "ordering_mismatches_vs_oracle": int((order_ok != order_ref).sum()), "arith": arith,
+              "note": "GPU vs CPU oracle (same arithmetic mode) on the cpu_baseline sample; bit-identical when values_differing == 0"}
     return {"value": img.size * len(SIGMAS) / dt / 1e9, "unit": "Gvoxel/s", "cores": cores,
             "kind": "port+reference-functor" if O.ref_available() else "port",
             "sample": "%dx%dx%d sub-volume of the same scan, all %d scales, %.1f s of CPU work "
                       "(ITK stages restated; per-voxel functor = reference header)" %
-                      (DIMS[0], DIMS[1], CPU_SAMPLE_NZ, len(SIGMAS), dt)}
+                      (DIMS[0], DIMS[1], CPU_SAMPLE_NZ, len(SIGMAS), dt)}, parity
 
 
 def run_slab(args, torch, dist, ctx, stream, dev, world, rank, local_rank, warmup, out_stream):
@@ -312,6 +331,7 @@ def _main(out_stream):
     ap.add_argument("--mask", default="ones", choices=["ones", "lung"])
     ap.add_argument("--arith", default="fma", choices=["fma", "plain"])
     ap.add_argument("--slab-size", type=int, default=1024)
+    ap.add_argument("--rois", type=int, default=0, help="hist workload: bin into N fixed-seed 41^3 ROIs (MakeBag) instead of the whole mask")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -350,7 +370,11 @@ def _main(out_stream):
         edges = np.tile(np.linspace(-1.0, 1.0, 40, dtype=np.float32), (len(SIGMAS) * 8, 1))
         edges[0::8] = np.linspace(-1100, 0, 40)       # blur rows
         edges[1::8] = np.linspace(0, 200, 40)         # gradient magnitude rows
-        counts = torch.zeros((1, len(SIGMAS) * 8, 41), dtype=torch.int32, device=dev)
+        rois = None
+        if args.rois > 0:
+            import synth
+            rois = synth.random_rois(mask.cpu().numpy(), args.rois, (41, 41, 41), seed=7)
+        counts = torch.zeros((max(args.rois, 1), len(SIGMAS) * 8, 41), dtype=torch.int32, device=dev)
         out = None
     else:
         out = torch.empty((len(SIGMAS), 8, nz, ny, nx), dtype=torch.float32, device=dev)
@@ -358,7 +382,7 @@ def _main(out_stream):
 
     def step():
         if hist:
-            ctx.emphysema_histograms_dev(img.data_ptr(), mask.data_ptr(), counts.data_ptr(), DIMS, SIGMAS, edges)
+            ctx.emphysema_histograms_dev(img.data_ptr(), mask.data_ptr(), counts.data_ptr(), DIMS, SIGMAS, edges, rois)
         else:
             ctx.emphysema_features_dev(img.data_ptr(), mask.data_ptr(), out.data_ptr(), DIMS, SIGMAS)
 
@@ -427,14 +451,17 @@ def _main(out_stream):
         dims_c, sp_c = (C.c_int * 3)(*DIMS), (C.c_double * 3)(1, 1, 1)
         sig_c = (C.c_double * len(SIGMAS))(*SIGMAS)
         if hist:
-            h_counts = np.zeros((1, len(SIGMAS) * 8, 41), np.uint32)
+            h_counts = np.zeros((max(args.rois, 1), len(SIGMAS) * 8, 41), np.uint32)
+            rois_c = None if rois is None else np.ascontiguousarray(rois, np.int32)
             d2h = h_counts.nbytes
             del counts
 
             def e2e_step():
                 rc = L.ife_cuda_emphysema_histograms(ctx.h, C.c_void_p(h_img.data_ptr()), C.c_void_p(h_mask.data_ptr()),
                                                      dims_c, sp_c, sig_c, len(SIGMAS), edges.ctypes.data_as(C.c_void_p), 40,
-                                                     None, 0, h_counts.ctypes.data_as(C.c_void_p), ife_b200.MEM_HOST)
+                                                     None if rois_c is None else rois_c.ctypes.data_as(C.c_void_p),
+                                                     0 if rois_c is None else len(rois_c),
+                                                     h_counts.ctypes.data_as(C.c_void_p), ife_b200.MEM_HOST)
                 ctx._check(rc)
         else:
             del out
@@ -466,9 +493,9 @@ def _main(out_stream):
                "h2d_bytes_per_step": int(h_img.numel() * 4 + h_mask.numel()), "d2h_bytes_per_step": int(d2h),
                "api": "ife_cuda_emphysema_%s(..., IFE_MEM_HOST) with pinned host buffers" % ("histograms" if hist else "features")}
 
-    cpu = None
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(torch, img, mask)
+        cpu, parity = cpu_baseline(torch, img, mask, ctx, args.arith)
 
     if rank == 0:
         out_stream.emit(json.dumps({
@@ -476,11 +503,13 @@ def _main(out_stream):
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 recursion / f32 stencil+solver", "data": "synthetic",
             "config": {"workload": ("ExtractFeatures multi-scale eigen features (8 masked feature volumes per scale)"
-                                    if not hist else "MakeBag-style: same features binned into DenseHistograms, no feature volumes written")
+                                    if not hist else "MakeBag-style: same features binned into DenseHistograms (%s), no feature volumes written"
+                                    % ("whole mask" if not args.rois else "%d ROIs of 41^3" % args.rois))
                                    + " on one 512x512x400 float CT-like scan per GPU, sigma{0.6,1.2,2.4,4.8}",
                        "mask": args.mask, "arith": args.arith, "parallelism": "1 scan per GPU, no data-path collective",
                        "l2": "inputs (525 MB/scan) and every intermediate are larger than the 126 MB L2; no flush needed"},
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity, "gpu_launches": launches,
+            "clocks": clocks,
         }))
     ctx.close()
     if dist:
