@@ -763,6 +763,93 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
   return IFE_OK;
 }
 
+int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const float* const* images,
+                                        const uint8_t* const* masks, const int dims[3],
+                                        const double spacing[3], const double* sigmas, int n_sigma,
+                                        const float* edges, int n_edges, const int* rois, int n_roi,
+                                        uint32_t* counts) {
+  if (!ctx) return IFE_E_INVALID;
+  if (n_scans <= 0) return IFE_OK;
+  if (!images || !masks || !counts || !edges) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  if (!sigmas || n_sigma <= 0) return fail(ctx, IFE_E_INVALID, "need at least one scale");
+  if (n_edges <= 0) return fail(ctx, IFE_E_INVALID, "need at least one histogram edge");
+  if (n_roi < 0 || (n_roi > 0 && !rois)) return fail(ctx, IFE_E_INVALID, "bad ROI list");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int nx = dims[0], ny = dims[1], nz = dims[2];
+  const size_t n = (size_t)nx * ny * nz;
+  for (int i = 0; i < n_scans; ++i)
+    if (!images[i] || !masks[i]) return fail(ctx, IFE_E_INVALID, "scan %d: null image or mask", i);
+  for (int r = 0; r < n_scans * n_roi; ++r) {
+    const int* b = rois + 6 * r;
+    if (b[0] < 0 || b[1] < 0 || b[2] < 0 || b[3] <= 0 || b[4] <= 0 || b[5] <= 0 ||
+        b[0] + b[3] > nx || b[1] + b[4] > ny || b[2] + b[5] > nz)
+      return fail(ctx, IFE_E_INVALID, "ROI %d is not inside the image", r);
+  }
+  Workspace& ws = ctx->ws;
+  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nz));
+  IFE_TRY(ws.blur.reserve(ctx, n * sizeof(float)));
+  // two upload slots: the H2D copy of scan i+1 (copy stream) runs behind the kernels of scan i
+  DeviceBuffer* img_slot[2] = {&ws.in_img, &ws.out[0]};
+  DeviceBuffer* mask_slot[2] = {&ws.in_mask, &ws.out[1]};
+  for (int k = 0; k < 2; ++k) {
+    IFE_TRY(img_slot[k]->reserve(ctx, n * sizeof(float)));
+    IFE_TRY(mask_slot[k]->reserve(ctx, n));
+  }
+  const int rows = n_sigma * 8, nb = n_edges + 1, R = std::max(n_roi, 1);
+  const size_t n_counts = (size_t)R * rows * nb;
+  IFE_TRY(ws.edges.reserve(ctx, (size_t)rows * n_edges * sizeof(float)));
+  IFE_TRY(ws.counts.reserve(ctx, 2 * n_counts * sizeof(uint32_t)));
+  if (n_roi > 0) IFE_TRY(ws.rois.reserve(ctx, (size_t)n_scans * n_roi * 6 * sizeof(int)));
+  cudaStream_t st = ctx->stream(), cp = ctx->copy_stream;
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ws.edges.ptr, edges, (size_t)rows * n_edges * sizeof(float),
+                                    cudaMemcpyHostToDevice, st));
+  if (n_roi > 0)
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ws.rois.ptr, rois, (size_t)n_scans * n_roi * 6 * sizeof(int),
+                                      cudaMemcpyHostToDevice, st));
+  // events[0..1]: upload of slot k done; events[2..3]: kernels reading slot k done
+  auto upload = [&](int i) -> int {
+    const int k = i & 1;
+    if (i >= 2) IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(cp, ctx->events[2 + k], 0));
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(img_slot[k]->ptr, images[i], n * sizeof(float), cudaMemcpyHostToDevice, cp));
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_slot[k]->ptr, masks[i], n, cudaMemcpyHostToDevice, cp));
+    IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[k], cp));
+    return IFE_OK;
+  };
+  IFE_TRY(upload(0));
+  const StencilCoef S = make_stencil_coef(spacing);
+  for (int i = 0; i < n_scans; ++i) {
+    const int k = i & 1;
+    if (i + 1 < n_scans) IFE_TRY(upload(i + 1));
+    IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->events[k], 0));
+    const float* d_img = (const float*)img_slot[k]->ptr;
+    const uint8_t* d_mask = (const uint8_t*)mask_slot[k]->ptr;
+    uint32_t* d_counts = (uint32_t*)ws.counts.ptr + (size_t)k * n_counts;
+    IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), st));
+    for (int s = 0; s < n_sigma; ++s) {
+      float* blur = (float*)ws.blur.ptr;
+      IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
+                            nullptr, nullptr));
+      FeatArgs A;
+      std::memset(&A, 0, sizeof(A));
+      A.vol = blur; A.mask_u8 = d_mask;
+      A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
+      A.hist.edges = (const float*)ws.edges.ptr + (size_t)s * 8 * n_edges;
+      A.hist.counts = d_counts + (size_t)s * 8 * nb;
+      A.hist.rois = n_roi > 0 ? (const int*)ws.rois.ptr + (size_t)i * n_roi * 6 : nullptr;
+      A.hist.n_roi = n_roi; A.hist.n_edges = n_edges;
+      A.hist.stride_roi = (long long)rows * nb;
+      IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+    }
+    IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[2 + k], st));
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts + (size_t)i * n_counts, d_counts, n_counts * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, st));
+  }
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(cp));
+  return IFE_OK;
+}
+
 int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const float* edges,
                        int n_edges, uint32_t* counts, int mem) {
   if (!ctx) return IFE_E_INVALID;

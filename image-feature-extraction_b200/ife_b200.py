@@ -69,6 +69,7 @@ def load_library():
     L.ife_cuda_hessian_eigen_features.argtypes = [vp, vp, vp, vp, ip, dp, d, i, i]
     L.ife_cuda_emphysema_features.argtypes = [vp, vp, vp, vp, ip, dp, dp, i, i]
     L.ife_cuda_emphysema_histograms.argtypes = [vp, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp, i]
+    L.ife_cuda_emphysema_histograms_batch.argtypes = [vp, i, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp]
     L.ife_cuda_histogram.argtypes = [vp, vp, sz, vp, i, vp, i]
     L.ife_cuda_eigen_features_batch.argtypes = [vp, vp, vp, sz, i]
     L.ife_cuda_sort_f32.argtypes = [vp, vp, sz, i]
@@ -256,6 +257,24 @@ class Context:
             self.h, _ptr(img), _ptr(mask), _i3(_dims_of(img)), _d3(spacing), _dn(sigmas),
             len(sigmas), _ptr(edges), edges.shape[1], _ptr(r), 0 if r is None else R,
             _ptr(counts), MEM_HOST))
+        return counts
+
+    def emphysema_histograms_batch(self, images, masks, sigmas, edges, rois=None, spacing=None):
+        """images / masks: lists of equally shaped (nz, ny, nx) host arrays (pinned memory makes
+        the upload overlap real); rois: (n_scans, R, 6) or None -> counts (n_scans, R|1, S*8, E+1)"""
+        images = [np.ascontiguousarray(a, np.float32) for a in images]
+        masks = [np.ascontiguousarray(m, np.uint8) for m in masks]
+        n = len(images)
+        sigmas = list(sigmas)
+        edges = np.ascontiguousarray(edges, np.float32).reshape(len(sigmas) * 8, -1)
+        r = None if rois is None else np.ascontiguousarray(rois, np.int32).reshape(n, -1, 6)
+        R = 1 if r is None else r.shape[1]
+        counts = np.zeros((n, R, len(sigmas) * 8, edges.shape[1] + 1), np.uint32)
+        ip_ = (C.c_void_p * n)(*[a.ctypes.data for a in images])
+        mp_ = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+        self._check(self.L.ife_cuda_emphysema_histograms_batch(
+            self.h, n, ip_, mp_, _i3(_dims_of(images[0])), _d3(spacing), _dn(sigmas), len(sigmas),
+            _ptr(edges), edges.shape[1], _ptr(r), 0 if r is None else R, _ptr(counts)))
         return counts
 
     def histogram(self, values, edges):

@@ -163,6 +163,19 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
                                   int n_edges, const int* rois, int n_roi, uint32_t* counts,
                                   int mem);
 
+/* A batch of scans of identical size (BASELINE.json configs[4]: "batch of scans, full
+ * multi-scale feature + histogram bagging pipeline"): ife_cuda_emphysema_histograms for
+ * n_scans host-resident scans, with the upload of scan i+1 overlapped with the kernels of
+ * scan i (pinned host memory makes the overlap real).  images / masks: arrays of n_scans
+ * host pointers; rois: [n_scans][n_roi][6] (each scan its own ROIs) or NULL with
+ * n_roi == 0; counts: [n_scans][max(n_roi,1)][n_sigma*8][n_edges+1], host.  One scan per
+ * GPU is the multi-GPU sharding of this workload: one context and one call per GPU. */
+int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const float* const* images,
+                                        const uint8_t* const* masks, const int dims[3],
+                                        const double spacing[3], const double* sigmas, int n_sigma,
+                                        const float* edges, int n_edges, const int* rois, int n_roi,
+                                        uint32_t* counts);
+
 /* DenseHistogram<float>::insert over an array (include/ife/Statistics/DenseHistogram.h:
  * 47-53): counts[n_edges+1] is overwritten. */
 int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const float* edges,

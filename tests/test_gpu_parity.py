@@ -264,6 +264,19 @@ def test_emphysema_histograms_whole_mask_and_rois(ctx, oracle):
     assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).sum() <= 2
 
 
+def test_histograms_batch_equals_one_call_per_scan(ctx):
+    shape = (24, 32, 40)
+    sigmas = [0.6, 1.2]
+    imgs = [synth.ct_like(shape, seed=80 + i, n_blobs=5) for i in range(3)]
+    mask = synth.clamp01(synth.lung_mask(shape))
+    edges = np.tile(np.linspace(-60, 60, 12, dtype=np.float32), (16, 1))
+    rois = np.stack([synth.random_rois(mask, 4, (9, 7, 5), seed=i) for i in range(3)])
+    one = np.stack([ctx.emphysema_histograms(im, mask, sigmas, edges) for im in imgs])
+    assert np.array_equal(ctx.emphysema_histograms_batch(imgs, [mask] * 3, sigmas, edges), one)
+    one = np.stack([ctx.emphysema_histograms(im, mask, sigmas, edges, rois[i]) for i, im in enumerate(imgs)])
+    assert np.array_equal(ctx.emphysema_histograms_batch(imgs, [mask] * 3, sigmas, edges, rois), one)
+
+
 def test_bad_arguments_are_rejected(ctx):
     import ctypes
     import ife_b200
