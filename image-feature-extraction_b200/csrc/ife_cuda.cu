@@ -15,6 +15,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "eigen_features.cuh"
+#include "features_march.cuh"
 #include "recursive_gaussian.cuh"
 #include "ife_ctx.h"
 
@@ -325,10 +326,16 @@ int reserve_smoothing(ife_cuda_ctx* ctx, int nf, int nx, int ny, int nzb) {
 // ---------------------------------------------------------------------------------------
 template <int MODE, bool HIST>
 void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                       const StencilCoef& S, const FeatArgs& A) {
+                       const StencilCoef& S, const FeatArgs& A, int zchunk) {
   constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
   bool all = true;
   for (int k = 0; k < NFEAT; ++k) all = all && A.out[k] != nullptr;
+  if (zchunk > 0) {   // z-marching kernel (everything but ROI-list histograms)
+    if (all && unit) features_march_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A, zchunk);
+    else if (unit) features_march_kernel<MODE, HIST, true, false><<<grid, block, smem, st>>>(S, A, zchunk);
+    else features_march_kernel<MODE, HIST, false, false><<<grid, block, smem, st>>>(S, A, zchunk);
+    return;
+  }
   if (all && unit) features_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A);
   else if (unit) features_kernel<MODE, HIST, true, false><<<grid, block, smem, st>>>(S, A);
   else features_kernel<MODE, HIST, false, false><<<grid, block, smem, st>>>(S, A);
@@ -341,7 +348,19 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
   const int nzo = A.zb1 - A.zb0;
   if (nzo <= 0 || A.nx <= 0 || A.ny <= 0) return IFE_OK;
   const dim3 block(kTX, kTY, 1);
-  const dim3 grid((A.nx + kTX - 1) / kTX, (A.ny + kTY - 1) / kTY, (nzo + kTZ - 1) / kTZ);
+  dim3 grid((A.nx + kTX - 1) / kTX, (A.ny + kTY - 1) / kTY, (nzo + kTZ - 1) / kTZ);
+  // ROI-list histograms keep the brick kernel (bricks that touch no ROI exit at once);
+  // everything else marches 32x8 columns in z, in chunks sized for >= ~8 waves of blocks
+  int zchunk = 0;
+  if (!(hist && A.hist.n_roi > 0) && !A.mask_f32 && (long long)A.nx * A.ny < (1LL << 28)) {
+    static_assert(kMX == kTX && kMY == kTY, "both kernels use a 32x8 footprint");
+    const long long cols = (long long)grid.x * grid.y;
+    const long long want = (8LL * 4 * ctx->sm_count + cols - 1) / cols;   // chunks per column
+    zchunk = (int)std::max<long long>(16, (nzo + want - 1) / want);
+    zchunk = std::min(zchunk, nzo);
+    zchunk = (int)std::min<long long>(zchunk, (1LL << 31) / ((long long)A.nx * A.ny) - 2);   // 32-bit offsets
+    grid.z = (nzo + zchunk - 1) / zchunk;
+  }
   if (grid.y > 65535 || grid.z > 65535) return fail(ctx, IFE_E_INVALID, "volume too large for the launch grid");
   const size_t smem =
       hist ? (size_t)nfeat * (A.hist.n_edges * sizeof(float) + (A.hist.n_edges + 1) * sizeof(uint32_t))
@@ -351,14 +370,14 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
   cudaStream_t st = ctx->stream();
   ProfScope prof(ctx, mode == 2 ? K_OTHER : K_FEATURES);
   if (mode == 0) {
-    if (hist) launch_features_t<0, true>(unit_spacing, grid, block, smem, st, S, A);
-    else launch_features_t<0, false>(unit_spacing, grid, block, 0, st, S, A);
+    if (hist) launch_features_t<0, true>(unit_spacing, grid, block, smem, st, S, A, zchunk);
+    else launch_features_t<0, false>(unit_spacing, grid, block, 0, st, S, A, zchunk);
   } else if (mode == 1) {
-    if (hist) launch_features_t<1, true>(unit_spacing, grid, block, smem, st, S, A);
-    else launch_features_t<1, false>(unit_spacing, grid, block, 0, st, S, A);
+    if (hist) launch_features_t<1, true>(unit_spacing, grid, block, smem, st, S, A, zchunk);
+    else launch_features_t<1, false>(unit_spacing, grid, block, 0, st, S, A, zchunk);
   } else {
-    if (hist) launch_features_t<2, true>(unit_spacing, grid, block, smem, st, S, A);
-    else launch_features_t<2, false>(unit_spacing, grid, block, 0, st, S, A);
+    if (hist) launch_features_t<2, true>(unit_spacing, grid, block, smem, st, S, A, zchunk);
+    else launch_features_t<2, false>(unit_spacing, grid, block, 0, st, S, A, zchunk);
   }
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
@@ -921,7 +940,7 @@ int ife_cuda_eigen_features_batch(ife_cuda_ctx* ctx, const float* A6, float* out
     IFE_TRY(ctx->ws.out[0].reserve(ctx, 6 * n * sizeof(float)));
     d_out = (float*)ctx->ws.out[0].ptr;
   }
-  eigen_features_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream()>>>(d_in, d_out, n);
+  eigen_features_batch_lean_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream()>>>(d_in, d_out, n);
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
   if (mem == IFE_MEM_HOST) {
