@@ -19,33 +19,43 @@
 //    integer min-reduction and one branch per voxel; voxels that fail it -- denormal or
 //    huge operands -- take the out-of-line IEEE routine.
 #pragma once
+#include "cp_async.cuh"
 #include "eigen_features.cuh"
 
 namespace ife {
 
-constexpr int kMX = 32, kMY = 8;          // the block's (x, y) footprint
+constexpr int kMX = 32, kMY = 4;          // the block's (x, y) footprint
 constexpr int kMPX = kMX + 2, kMPY = kMY + 2;
 constexpr int kMPlane = kMPX * kMPY;      // 340 staged values per plane
 
 // what a voxel carries from its own plane
 struct PlaneTerms {
   double cD;        // centre value
+  double g2;        // gx^2 + gy^2 of GradientMagnitudeImageFilter (double)
+  float c;
   float Dx, Dy;     // first derivatives (DerivativeImageFilter output, float)
   float Dxx, Dyy, Dxy;
-  double g2;        // gx^2 + gy^2 of GradientMagnitudeImageFilter (double)
+  bool inside;      // in the image, in the output range and in the mask
+  unsigned mraw;    // this plane's mask byte, fetched two steps ahead of its use
 };
+
+// keeps the compiler from testing a prefetched value the moment it arrives (which would stall
+// on the load an iteration early): the value stays opaque until the statement executes
+__device__ __forceinline__ unsigned opaque_u32(unsigned v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
 
 // MODE / HIST / UNIT / ALLOUT as in features_kernel.  HIST here is the whole-volume
 // histogram only (A.hist.n_roi == 0); ROI lists stay with the brick kernel, whose culling of
 // bricks that touch no ROI is worth more than the march.  Masks: uint8 or none.
-// Host-checked: zchunk * nx * ny < 2^31 (32-bit offsets relative to per-block base pointers).
 template <int MODE, bool HIST, bool UNIT, bool ALLOUT>
-__global__ void __launch_bounds__(kMX * kMY)
+__global__ void __launch_bounds__(kMX * kMY, 1024 / (kMX * kMY))
 features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_constant__ FeatArgs A,
                       const int zchunk) {
   constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
   constexpr int NT = kMX * kMY;
-  __shared__ float plane[2][kMPlane];
+  __shared__ float plane[4][kMPlane];   // ring: plane pz+2 lands while plane pz is consumed
   extern __shared__ unsigned char feat_smem[];
   float* s_edges = reinterpret_cast<float*>(feat_smem);
   uint32_t* s_counts = reinterpret_cast<uint32_t*>(s_edges + NFEAT * A.hist.n_edges);
@@ -57,76 +67,88 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   }
 
   const int nx = A.nx, ny = A.ny;
-  const unsigned psz = (unsigned)nx * (unsigned)ny;          // plane stride (elements)
+  const size_t psz = (size_t)nx * (size_t)ny;                // plane stride (elements)
   const int x0 = blockIdx.x * kMX, y0 = blockIdx.y * kMY;
   const int zs = A.zb0 + blockIdx.z * zchunk;
   const int ze = min(zs + zchunk, A.zb1);                    // output planes [zs, ze)
   const int zlo = max(zs - 1, 0);                            // first plane this block touches
-  // block-uniform base pointers; everything below is a 32-bit offset from them
-  const float* __restrict__ vol = A.vol + (size_t)psz * zlo;
-  const uint8_t* __restrict__ mask = A.mask_u8 ? A.mask_u8 + (size_t)psz * zlo : nullptr;
-  float* outp[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    outp[k] = (k < NFEAT && A.out[k]) ? A.out[k] + ((size_t)psz * (zs - A.zb0) + (size_t)nx * y0 + x0) : nullptr;
 
-  // staging slots of this thread: element tid and (for the first 84 threads) tid + 256 of
-  // the padded 34x10 plane; the x/y clamps live in these loop-invariant offsets
+  // staging slots of this thread: elements tid and (while inside the padded (kMX+2) x (kMY+2)
+  // plane) tid + NT; the x/y clamps live in these loop-invariant offsets
   const int e0r = tid / kMPX, e0c = tid - e0r * kMPX;
   const int e1 = min(tid + NT, kMPlane - 1);
   const bool has1 = tid + NT < kMPlane;
   const int e1r = e1 / kMPX, e1c = e1 - e1r * kMPX;
-  const unsigned g0 = (unsigned)min(max(x0 - 1 + e0c, 0), nx - 1) + (unsigned)nx * (unsigned)min(max(y0 - 1 + e0r, 0), ny - 1);
-  const unsigned g1 = (unsigned)min(max(x0 - 1 + e1c, 0), nx - 1) + (unsigned)nx * (unsigned)min(max(y0 - 1 + e1r, 0), ny - 1);
-
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
   const bool in_xy = x < nx && y < ny;
-  const unsigned vox_xy = in_xy ? (unsigned)x + (unsigned)nx * (unsigned)y : 0u;   // mask offset in a plane
-  const unsigned out_xy = threadIdx.x + (unsigned)nx * threadIdx.y;              // relative to outp[]
-  const int lc = (threadIdx.y + 1) * kMPX + threadIdx.x + 1;                       // centre in the padded plane
-  const int zlast = A.nzb - 1 - zlo;                                               // last plane, relative to zlo
+  const bool has_mask = A.mask_u8 != nullptr;
+  // running pointers: plane `pz+1` of the two staged elements and of this voxel's mask byte
+  const float* p0 = A.vol + psz * zlo + (size_t)min(max(x0 - 1 + e0c, 0), nx - 1) +
+                    (size_t)nx * (size_t)min(max(y0 - 1 + e0r, 0), ny - 1);
+  const float* p1 = A.vol + psz * zlo + (size_t)min(max(x0 - 1 + e1c, 0), nx - 1) +
+                    (size_t)nx * (size_t)min(max(y0 - 1 + e1r, 0), ny - 1);
+  const uint8_t* pm = (has_mask ? A.mask_u8 : reinterpret_cast<const uint8_t*>(A.vol)) + psz * zlo +
+                      (in_xy ? (size_t)x + (size_t)nx * (size_t)y : 0);
+  // output pointer of plane 0 of this voxel; the other planes are uniform byte offsets away
+  const size_t o_first = psz * (size_t)(zs - A.zb0) + (size_t)nx * (size_t)y + (size_t)x;
+  int first_out = 0;
+#pragma unroll
+  for (int k = NFEAT - 1; k >= 0; --k)
+    if (A.out[k]) first_out = k;
+  float* po = A.out[first_out] ? A.out[first_out] + o_first : nullptr;
+  long long dk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    dk[k] = (k < NFEAT && A.out[k]) ? (long long)(A.out[k] - A.out[first_out]) : 0;
+  const int lc = (threadIdx.y + 1) * kMPX + threadIdx.x + 1;  // centre in the padded plane
 
-  // software pipeline, one plane per iteration:  registers (v0, v1, mraw) hold plane `pz`
-  // (fetched an iteration ago) -> shared memory -> in-plane terms N; the voxel of plane
-  // pz-1 is finished from (P, C, N).  Planes zs-1 and ze only feed their neighbours.
-  float v0, v1;
-  unsigned mraw = 0;
-  v0 = __ldg(vol + g0);                     // plane zs-1 clamped = plane zlo
-  v1 = has1 ? __ldg(vol + g1) : 0.0f;
-  PlaneTerms P, C;
-  bool insideC = false;
-  P.cD = 0.0; P.Dx = P.Dy = 0.0f;
-  C.cD = 0.0; C.Dx = C.Dy = C.Dxx = C.Dyy = C.Dxy = 0.0f; C.g2 = 0.0;
-  float cC = 0.0f;
-  unsigned oz = out_xy - 2u * psz;          // output offset of plane pz-1 (first used at pz = zs+1)
-  int buf = 0;
-#pragma unroll 1
-  for (int pz = zs - 1; pz <= ze; ++pz) {
-    float* pl = plane[buf];
-    pl[tid] = v0;
-    if (has1) pl[e1] = v1;
+  // software pipeline, one plane per step.  Plane pz+2 is copied global -> shared with
+  // cp.async (two steps of work hide the HBM latency, no registers held), its mask byte
+  // goes into the PlaneTerms that will play the role of N two steps later; the in-plane
+  // terms N of plane pz are computed from shared memory and the voxel of plane pz-1 is
+  // finished from (P, C, N).  Planes zs-1 and ze only feed their neighbours.  A ring slot is
+  // rewritten two barriers after its last reader, so one barrier per plane is enough.
+  int pnext = zs - 1;                        // plane the pointers refer to (before clamping)
+  auto advance = [&]() {
+    if (pnext >= 0 && pnext < A.nzb - 1) { p0 += psz; p1 += psz; pm += psz; }
+    ++pnext;
+  };
+  auto issue = [&](int slot) {
+    cp_async4(&plane[slot][tid], p0);
+    if (has1) cp_async4(&plane[slot][e1], p1);
+    cp_async_commit();
+  };
+  PlaneTerms T0, T1, T2;
+  T0.cD = T1.cD = T2.cD = 0.0; T0.g2 = T1.g2 = T2.g2 = 0.0;
+  T0.c = T1.c = T2.c = 0.0f; T0.Dx = T1.Dx = T2.Dx = 0.0f; T0.Dy = T1.Dy = T2.Dy = 0.0f;
+  T0.Dxx = T1.Dxx = T2.Dxx = 0.0f; T0.Dyy = T1.Dyy = T2.Dyy = 0.0f; T0.Dxy = T1.Dxy = T2.Dxy = 0.0f;
+  T0.inside = T1.inside = T2.inside = false;
+  T0.mraw = T1.mraw = T2.mraw = 0u;
+  issue(0);                                  // plane zs-1
+  advance();
+  issue(1);                                  // plane zs; T0 is N at step zs
+  if (has_mask) T0.mraw = __ldg(pm);
+  advance();
+
+  auto step = [&](const int pz, const PlaneTerms& P, PlaneTerms& C, PlaneTerms& N) {
+    issue((pz - zs + 3) & 3);                // plane pz+2; C is N at step pz+2
+    if (has_mask) C.mraw = __ldg(pm);
+    advance();
     // mask of plane pz: false for the two feeder planes and outside the image
-    const bool m_own = in_xy && pz >= zs && pz < ze && (mask == nullptr || mraw != 0u);
-    {   // fetch plane pz+1 (clamped; one wasted fetch after the last plane) and its mask
-      const unsigned rel = (unsigned)min(pz + 1 - zlo, zlast);
-      const unsigned po = psz * rel;
-      v0 = __ldg(vol + (po + g0));
-      if (has1) v1 = __ldg(vol + (po + g1));
-      if (mask != nullptr) mraw = __ldg(mask + (po + vox_xy));
-    }
+    N.inside = in_xy && pz >= zs && pz < ze && (!has_mask || opaque_u32(N.mraw) != 0u);
+    cp_async_wait<2>();
     __syncthreads();
+    const float* pl = plane[(pz - zs + 1) & 3];
 
     // ---- in-plane terms of plane pz ----
-    PlaneTerms N;
     const float c000 = pl[lc];
     const float xm = pl[lc - 1], xp = pl[lc + 1];
     const float ym = pl[lc - kMPX], yp = pl[lc + kMPX];
+    N.c = c000;
     N.cD = (double)c000;
     N.Dx = deriv1<UNIT>(S.d1[0], xm, xp);
     N.Dy = deriv1<UNIT>(S.d1[1], ym, yp);
-    N.Dxx = N.Dyy = N.Dxy = 0.0f;
-    N.g2 = 0.0;
-    if (m_own) {
+    if (N.inside) {
       const double dxm = (double)xm, dxp = (double)xp, dym = (double)ym, dyp = (double)yp;
       if (MODE == 0 || MODE == 1) {
         N.Dxx = deriv2<UNIT>(S.d2a[0], S.d2b[0], dxm, N.cD, dxp);
@@ -150,26 +172,24 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
     // ---- finish the voxel of plane z = pz-1 (planes P, C, N) ----
     if (pz > zs) {
       float f[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = 0.0f;
-      if (insideC) {
+      if (C.inside) {
         if (MODE == 0 || MODE == 2) {
           // sqrt of a sum of squares of float differences: zero or far inside the double range
-          double a2, scale;
+          float gm;
           if (UNIT) {
             const double gz = __dsub_rn(N.cD, P.cD);
-            a2 = __dadd_rn(C.g2, __dmul_rn(gz, gz));
-            scale = 0.5;
-          } else {
+            const double a2 = __dadd_rn(C.g2, __dmul_rn(gz, gz));
+#if IFE_EXP == 2
+            gm = (float)(0.5 * a2);
+#else
+            gm = (float)(0.5 * dsqrt_rn_inrange(a2));
+#endif
+            gm = a2 > 0.0 ? gm : (float)a2;     // sqrt(+0) = +0 (a2 is never negative; NaN propagates)
+          } else {                              // arbitrary spacing: keep the general routine
             const double gz = __dadd_rn(__dmul_rn(-S.g1[2], P.cD), __dmul_rn(S.g1[2], N.cD));
-            a2 = __dadd_rn(C.g2, __dmul_rn(gz, gz));
-            scale = 1.0;
+            gm = (float)__dsqrt_rn(__dadd_rn(C.g2, __dmul_rn(gz, gz)));
           }
-          float gm;
-          if (UNIT) gm = (float)(scale * dsqrt_rn_inrange(a2));
-          else gm = (float)__dsqrt_rn(a2);      // arbitrary spacing: keep the general routine
-          gm = a2 > 0.0 ? gm : (float)a2;       // sqrt(+0) = +0 (a2 is never negative; NaN propagates)
-          if (MODE == 0) { f[0] = cC; f[1] = gm; } else f[0] = gm;
+          if (MODE == 0) { f[0] = C.c; f[1] = gm; } else f[0] = gm;
         }
         if (MODE == 0 || MODE == 1) {
           float H[6], e[6];
@@ -179,33 +199,56 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
           H[3] = C.Dyy;
           H[4] = A.dy_bug ? H[2] : deriv1<UNIT>(S.d1[2], P.Dy, N.Dy);    // Dyz = Dz(Dy)
           H[5] = deriv2<UNIT>(S.d2a[2], S.d2b[2], P.cD, C.cD, N.cD);     // Dzz
+#if IFE_EXP == 5
+#pragma unroll
+          for (int k = 0; k < 6; ++k) e[k] = H[k];
+#else
           eigen_features6_lean(H, e);
+#endif
           constexpr int o6 = MODE == 0 ? 2 : 0;
 #pragma unroll
           for (int k = 0; k < 6; ++k) f[o6 + k] = e[k];
         }
-      }
-      if (in_xy) {
+#if IFE_EXP == 4
+        { float ssum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < NFEAT; ++k) ssum += f[k];
+          *po = ssum; }
+#else
 #pragma unroll
         for (int k = 0; k < NFEAT; ++k)
-          if (ALLOUT || outp[k]) outp[k][oz] = f[k];
+          if (ALLOUT || A.out[k]) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = f[k];
+#endif
+      } else {
+#pragma unroll
+        for (int k = 0; k < NFEAT; ++k) f[k] = 0.0f;
+        if (in_xy) {
+#pragma unroll
+          for (int k = 0; k < NFEAT; ++k)
+            if (ALLOUT || A.out[k]) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = 0.0f;
+        }
       }
       if (HIST) {
 #pragma unroll
         for (int k = 0; k < NFEAT; ++k) {
-          const int bin = insideC ? dense_bin(s_edges + k * A.hist.n_edges, A.hist.n_edges, f[k]) : 0;
-          hist_add(s_counts + k * nb, bin, insideC);
+          const int bin = C.inside ? dense_bin(s_edges + k * A.hist.n_edges, A.hist.n_edges, f[k]) : 0;
+          hist_add(s_counts + k * nb, bin, C.inside);
         }
       }
+      po += psz;
     }
+  };
 
-    P.cD = C.cD; P.Dx = C.Dx; P.Dy = C.Dy;
-    C = N;
-    cC = c000;
-    insideC = m_own;
-    oz += psz;
-    buf ^= 1;
+  // the three roles rotate through T0/T1/T2, so nothing is ever shifted between registers
+#pragma unroll 1
+  for (int pz = zs - 1; pz <= ze; pz += 3) {
+    step(pz, T0, T1, T2);
+    if (pz + 1 > ze) break;
+    step(pz + 1, T1, T2, T0);
+    if (pz + 2 > ze) break;
+    step(pz + 2, T2, T0, T1);
   }
+  cp_async_wait<0>();
 
   if (HIST) {
     __syncthreads();

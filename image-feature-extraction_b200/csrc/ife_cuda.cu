@@ -347,15 +347,17 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
   const int nfeat = mode == 0 ? 8 : (mode == 1 ? 6 : 1);
   const int nzo = A.zb1 - A.zb0;
   if (nzo <= 0 || A.nx <= 0 || A.ny <= 0) return IFE_OK;
-  const dim3 block(kTX, kTY, 1);
+  dim3 block(kTX, kTY, 1);
   dim3 grid((A.nx + kTX - 1) / kTX, (A.ny + kTY - 1) / kTY, (nzo + kTZ - 1) / kTZ);
   // ROI-list histograms keep the brick kernel (bricks that touch no ROI exit at once);
   // everything else marches 32x8 columns in z, in chunks sized for >= ~8 waves of blocks
   int zchunk = 0;
   if (!(hist && A.hist.n_roi > 0) && !A.mask_f32 && (long long)A.nx * A.ny < (1LL << 28)) {
-    static_assert(kMX == kTX && kMY == kTY, "both kernels use a 32x8 footprint");
+    block = dim3(kMX, kMY, 1);
+    grid.x = (A.nx + kMX - 1) / kMX;
+    grid.y = (A.ny + kMY - 1) / kMY;
     const long long cols = (long long)grid.x * grid.y;
-    const long long want = (8LL * 4 * ctx->sm_count + cols - 1) / cols;   // chunks per column
+    const long long want = (8LL * (1024 / (kMX * kMY)) * ctx->sm_count + cols - 1) / cols;   // chunks per column
     zchunk = (int)std::max<long long>(16, (nzo + want - 1) / want);
     zchunk = std::min(zchunk, nzo);
     zchunk = (int)std::min<long long>(zchunk, (1LL << 31) / ((long long)A.nx * A.ny) - 2);   // 32-bit offsets

@@ -31,6 +31,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "cp_async.cuh"
 #include "fdiv.cuh"
 
 namespace ife {
@@ -425,16 +426,6 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
 // recurrence allow.  Alignment requirements are checked on the host (else the plain
 // register-staged kernel runs).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 constexpr int kAsyncThreads = 128;
 constexpr int kYbsUnroll = 4;
 
@@ -465,9 +456,6 @@ __device__ __forceinline__ void stage_sample(const AsyncStage<NF, INMODE, L, CK>
   }
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
 
 // Issue the copies of chunk kc (planes i0-3+row_first .. i0+L-1, clipped to the line) into
 // stage S.  Warp-cooperative 16-byte copies: a warp's 32 lines are 128 contiguous bytes per

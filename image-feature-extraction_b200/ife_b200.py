@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libife_cuda.so")
+LIB_PATH = os.environ.get("IFE_CUDA_LIB") or os.path.join(_HERE, "lib", "libife_cuda.so")
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "ife_cuda.h"))
 
 MEM_HOST, MEM_DEVICE = 0, 1
