@@ -24,6 +24,9 @@
 
 namespace ife {
 
+#ifndef IFE_MARCH_MINB
+#define IFE_MARCH_MINB 8   // resident 128-thread blocks per SM the register budget is cut for
+#endif
 constexpr int kMX = 32, kMY = 4;          // the block's (x, y) footprint
 constexpr int kMPX = kMX + 2, kMPY = kMY + 2;
 constexpr int kMPlane = kMPX * kMPY;      // 340 staged values per plane
@@ -50,7 +53,7 @@ __device__ __forceinline__ unsigned opaque_u32(unsigned v) {
 // histogram only (A.hist.n_roi == 0); ROI lists stay with the brick kernel, whose culling of
 // bricks that touch no ROI is worth more than the march.  Masks: uint8 or none.
 template <int MODE, bool HIST, bool UNIT, bool ALLOUT>
-__global__ void __launch_bounds__(kMX * kMY, 1024 / (kMX * kMY))
+__global__ void __launch_bounds__(kMX * kMY, IFE_MARCH_MINB)
 features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_constant__ FeatArgs A,
                       const int zchunk) {
   constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);

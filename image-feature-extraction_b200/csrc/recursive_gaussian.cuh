@@ -164,6 +164,49 @@ template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, typename SRC, t
 __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& src, const SINK& sink,
                                                int i0, int len, int n, Rec (&cs)[NF],
                                                Rec (&as)[NF], YB& yb) {
+  if (!GENERIC) {
+    // Hot path.  The causal replay (forward through the chunk, from the checkpoint) and the
+    // anticausal recurrence (backward, from the state the chunk after left) are independent
+    // until their sum, so they run in the same loop from opposite ends: 2*NF independent
+    // dependency chains per thread instead of NF, which is what keeps the FP64 pipe busy at
+    // the few warps per SM the recurrence's registers allow.  In the first half both
+    // results are parked in yb (the slot of the other direction is still free); in the
+    // second half each new value meets its parked partner and the sample is emitted.
+    static_assert(L % 2 == 0, "chunk length must be even");
+    const Fb fc = fb_select(C.D, C.BN, 4);
+    const Fb fa = fb_select(C.D, C.BM, 4);
+    constexpr int U2 = UNROLL >= L ? L / 2 : UNROLL;
+#pragma unroll U2
+    for (int t = 0; t < L / 2; ++t) {
+      const int jc = t, ja = L - 1 - t;
+      double vc[NF], va[NF];
+      src(jc, vc);
+      src(ja, va);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        yb.set(f, jc, causal_step<FMA>(C, fc, cs[f], vc[f]));
+        yb.set(f, ja, anti_step<FMA>(C, fa, as[f], va[f]));
+      }
+    }
+#pragma unroll U2
+    for (int t = L / 2; t < L; ++t) {
+      const int jc = t, ja = L - 1 - t;
+      double vc[NF], va[NF];
+      src(jc, vc);
+      src(ja, va);
+      float oc[NF], oa[NF];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const double y = causal_step<FMA>(C, fc, cs[f], vc[f]);
+        const double w = anti_step<FMA>(C, fa, as[f], va[f]);
+        oc[f] = (float)__dadd_rn(y, yb.get(f, jc));      // parked anticausal value of jc
+        oa[f] = (float)__dadd_rn(yb.get(f, ja), w);      // parked causal value of ja
+      }
+      sink(jc, oc);
+      sink(ja, oa);
+    }
+    return;
+  }
   {
     Fb fb = fb_select(C.D, C.BN, 4);
 #pragma unroll UNROLL
