@@ -129,9 +129,11 @@ static int slab_compute(ife_cuda_ctx* ctx, const float* bimg, const uint8_t* bma
                         int z0, int z1, float* out, const int global_dims[3],
                         const double spacing[3], const double* sigmas, int n_sigma,
                         const float* edges, int n_edges, uint32_t* counts, double halo_factor,
-                        int mem, uint32_t** d_counts_out) {
+                        int mem, uint32_t** d_counts_out, cudaEvent_t far_ready = nullptr,
+                        int near_h = 0) {
   using namespace ife;
   cudaStream_t st = ctx->stream();
+  bool far_waited = far_ready == nullptr;
   Workspace& ws = ctx->ws;
   const int nx = global_dims[0], ny = global_dims[1], nz = global_dims[2];
   const size_t plane = (size_t)nx * ny;
@@ -162,6 +164,10 @@ static int slab_compute(ife_cuda_ctx* ctx, const float* bimg, const uint8_t* bma
   for (int s = 0; s < n_sigma; ++s) {
     // z-pass extent at this scale: the warm-up halo shrinks with sigma
     const int H = ife_cuda_slab_halo(sigmas[s], spacing[2], halo_factor);
+    if (!far_waited && H > near_h) {   // first scale that reads planes of the second exchange group
+      IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(st, far_ready, 0));
+      far_waited = true;
+    }
     const int sz0 = std::max(bz0, z0 - H), sz1 = std::min(bz1, z1 + H);
     float* blur = (float*)ws.blur.ptr;
     IFE_TRY(smooth_volume(ctx, bimg + plane * (sz0 - bz0), bmask + plane * (sz0 - bz0), true, blur, nx,
@@ -188,6 +194,7 @@ static int slab_compute(ife_cuda_ctx* ctx, const float* bimg, const uint8_t* bma
       IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n_own, d_out, 8 * n_own * sizeof(float),
                                         cudaMemcpyDeviceToHost, st));
   }
+  if (!far_waited) IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(st, far_ready, 0));
   return IFE_OK;
 }
 
@@ -278,6 +285,10 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
   IFE_TRY(ws.slab_mask.reserve(ctx, plane * nzb));
   float* bimg = (float*)ws.slab_img.ptr;
   uint8_t* bmask = (uint8_t*)ws.slab_mask.ptr;
+  cudaStream_t cs = ctx->copy_stream;
+  cudaEvent_t ev_own = ctx->events[0], ev_near = ctx->events[1], ev_far = ctx->events[2], ev_done = ctx->events[3];
+  // kernels of the previous call may still read the halo planes the receives overwrite
+  IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ev_done, 0));
   const cudaMemcpyKind kin = mem == IFE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   IFE_CUDA_TRY(ctx, cudaMemcpyAsync(bimg + plane * (z0 - bz0), image_slab, n_own * sizeof(float), kin, st));
   if (mask_slab)
@@ -285,33 +296,61 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
   else
     IFE_CUDA_TRY(ctx, cudaMemsetAsync(bmask + plane * (z0 - bz0), 1, n_own, st));
 
-  // ---- halo exchange: every pair of ranks whose (slab+halo) and slab overlap ----
+  // ---- halo exchange on the copy stream, in two groups: the planes the first scale needs
+  // (its halo is the smallest when scales ascend), then the rest, which arrives behind the
+  // kernels of the first scale.  Device-resident slabs are sent straight from the caller's
+  // buffers, so the exchange does not wait for the copy into the slab+halo buffer either.
+  cudaEvent_t far_ready = nullptr;
+  int near_h = Hmax;
   if (P > 1) {
-    IFE_NCCL_TRY(ctx, api.GroupStart());
-    for (int r = 0; r < P; ++r) {
-      if (r == me) continue;
-      int rz0, rz1;
-      slab_range(nz, P, r, &rz0, &rz1);
-      // planes I need from r: [bz0,bz1) minus my own, intersected with r's slab
-      const int n0 = std::max(bz0, rz0), n1 = std::min(bz1, rz1);
-      if (n0 < n1) {
-        IFE_NCCL_TRY(ctx, api.Recv(bimg + plane * (n0 - bz0), plane * (n1 - n0), ncclFloat, r, comm, st));
-        IFE_NCCL_TRY(ctx, api.Recv(bmask + plane * (n0 - bz0), plane * (n1 - n0), ncclUint8, r, comm, st));
-      }
-      // planes r needs from me (same Hmax on every rank)
-      const int rb0 = std::max(0, rz0 - Hmax), rb1 = std::min(nz, rz1 + Hmax);
-      const int s0 = std::max(rb0, z0), s1 = std::min(rb1, z1);
-      if (s0 < s1) {
-        IFE_NCCL_TRY(ctx, api.Send(bimg + plane * (s0 - bz0), plane * (s1 - s0), ncclFloat, r, comm, st));
-        IFE_NCCL_TRY(ctx, api.Send(bmask + plane * (s0 - bz0), plane * (s1 - s0), ncclUint8, r, comm, st));
-      }
+    const bool own_src = mem == IFE_MEM_DEVICE && mask_slab != nullptr;
+    const float* simg = own_src ? image_slab : bimg + plane * (z0 - bz0);
+    const uint8_t* smask = own_src ? mask_slab : bmask + plane * (z0 - bz0);
+    if (!own_src) {
+      IFE_CUDA_TRY(ctx, cudaEventRecord(ev_own, st));
+      IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ev_own, 0));
     }
-    IFE_NCCL_TRY(ctx, api.GroupEnd());
+    near_h = std::min(Hmax, ife_cuda_slab_halo(sigmas[0], spacing[2], halo_factor));
+    // planes at distance (hlo, hhi] outside each slab travel in one grouped call
+    auto exchange = [&](int hlo, int hhi) -> int {
+      IFE_NCCL_TRY(ctx, api.GroupStart());
+      for (int r = 0; r < P; ++r) {
+        if (r == me) continue;
+        int rz0, rz1;
+        slab_range(nz, P, r, &rz0, &rz1);
+        const bool above = rz0 >= z1;   // r's slab lies above mine (slabs are ordered)
+        // planes I need from r
+        int n0 = above ? std::max(z1 + hlo, rz0) : std::max(std::max(0, z0 - hhi), rz0);
+        int n1 = above ? std::min(std::min(nz, z1 + hhi), rz1) : std::min(z0 - hlo, rz1);
+        if (n0 < n1) {
+          IFE_NCCL_TRY(ctx, api.Recv(bimg + plane * (n0 - bz0), plane * (n1 - n0), ncclFloat, r, comm, cs));
+          IFE_NCCL_TRY(ctx, api.Recv(bmask + plane * (n0 - bz0), plane * (n1 - n0), ncclUint8, r, comm, cs));
+        }
+        // planes r needs from me: I am below r exactly when r is above me
+        int s0 = above ? std::max(std::max(0, rz0 - hhi), z0) : std::max(rz1 + hlo, z0);
+        int s1 = above ? std::min(rz0 - hlo, z1) : std::min(std::min(nz, rz1 + hhi), z1);
+        if (s0 < s1) {
+          IFE_NCCL_TRY(ctx, api.Send(simg + plane * (s0 - z0), plane * (s1 - s0), ncclFloat, r, comm, cs));
+          IFE_NCCL_TRY(ctx, api.Send(smask + plane * (s0 - z0), plane * (s1 - s0), ncclUint8, r, comm, cs));
+        }
+      }
+      IFE_NCCL_TRY(ctx, api.GroupEnd());
+      return IFE_OK;
+    };
+    IFE_TRY(exchange(0, near_h));
+    IFE_CUDA_TRY(ctx, cudaEventRecord(ev_near, cs));
+    if (near_h < Hmax) {
+      IFE_TRY(exchange(near_h, Hmax));
+      IFE_CUDA_TRY(ctx, cudaEventRecord(ev_far, cs));
+      far_ready = ev_far;
+    }
+    IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_near, 0));
   }
 
   uint32_t* d_counts = nullptr;
   IFE_TRY(slab_compute(ctx, bimg, bmask, bz0, bz1, z0, z1, out, global_dims, spacing, sigmas, n_sigma,
-                       edges, n_edges, counts, halo_factor, mem, &d_counts));
+                       edges, n_edges, counts, halo_factor, mem, &d_counts, far_ready, near_h));
+  IFE_CUDA_TRY(ctx, cudaEventRecord(ev_done, st));
 
   // ---- combine the per-rank histograms ----
   if (edges) {
