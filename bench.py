@@ -123,6 +123,36 @@ def synth_scan_torch(torch, device, seed, mask_kind):
     return img, mask
 
 
+def equalized_edges_from_scan(torch, ctx, img, mask, n_edges):
+    """40 equal-frequency edges per (scale, feature), as MakeBag gets them from
+    DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures: quantiles of a 2 M-voxel sample of
+    the in-mask feature values of this scan (set-up, outside the timed region)."""
+    import numpy as np
+    nx, ny, nz = DIMS
+    dev = img.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    inside = torch.nonzero(mask.reshape(-1), as_tuple=False).reshape(-1)
+    pick = inside[torch.randint(0, inside.numel(), (2_000_000,), generator=g, device=dev)]
+    q = torch.linspace(0.0, 1.0, n_edges + 2, device=dev, dtype=torch.float64)[1:-1]
+    feats = torch.empty((1, 8, nz, ny, nx), dtype=torch.float32, device=dev)
+    rows = []
+    for s in SIGMAS:
+        ctx.emphysema_features_dev(img.data_ptr(), mask.data_ptr(), feats.data_ptr(), DIMS, [s])
+        ctx.synchronize()
+        for k in range(8):
+            v = torch.sort(feats[0, k].reshape(-1)[pick].to(torch.float64)).values
+            rows.append(v[(q * (v.numel() - 1)).long()].to(torch.float32))
+    del feats
+    edges = torch.stack(rows).cpu().numpy()
+    # strictly increasing rows keep every bin meaningful even where a feature saturates
+    for r in edges:
+        for j in range(1, len(r)):
+            if not r[j] > r[j - 1]:
+                r[j] = np.nextafter(r[j - 1], np.float32(np.inf))
+    return np.ascontiguousarray(edges, np.float32)
+
+
 def run_reference(args, out_stream):
     """--impl reference: the reference's CPU path (oracle port; ITK itself cannot be built in
     this image) on this box's host cores, same metric/config, each step a bounded sample."""
@@ -367,9 +397,7 @@ def _main(out_stream):
     hist = args.workload == "hist"
     edges = None
     if hist:
-        edges = np.tile(np.linspace(-1.0, 1.0, 40, dtype=np.float32), (len(SIGMAS) * 8, 1))
-        edges[0::8] = np.linspace(-1100, 0, 40)       # blur rows
-        edges[1::8] = np.linspace(0, 200, 40)         # gradient magnitude rows
+        edges = equalized_edges_from_scan(torch, ctx, img, mask, 40)
         rois = None
         if args.rois > 0:
             import synth

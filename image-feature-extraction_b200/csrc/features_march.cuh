@@ -27,7 +27,17 @@ namespace ife {
 #ifndef IFE_MARCH_MINB
 #define IFE_MARCH_MINB 8   // resident 128-thread blocks per SM the register budget is cut for
 #endif
-constexpr int kMX = 32, kMY = 4;          // the block's (x, y) footprint
+#ifndef IFE_MARCH_MINB_HIST
+#define IFE_MARCH_MINB_HIST 5   // histogram variant: 42 KB of private counters per block
+#endif
+constexpr int kMX = 32, kMY = 4;
+
+// smallest power of two above n_edges (edge rows are padded with +inf up to it)
+__host__ __device__ inline int hist_edge_pitch(int n_edges) {
+  int ep = 2;
+  while (ep <= n_edges) ep <<= 1;
+  return ep;
+}          // the block's (x, y) footprint
 constexpr int kMPX = kMX + 2, kMPY = kMY + 2;
 constexpr int kMPlane = kMPX * kMPY;      // 340 staged values per plane
 
@@ -53,20 +63,31 @@ __device__ __forceinline__ unsigned opaque_u32(unsigned v) {
 // histogram only (A.hist.n_roi == 0); ROI lists stay with the brick kernel, whose culling of
 // bricks that touch no ROI is worth more than the march.  Masks: uint8 or none.
 template <int MODE, bool HIST, bool UNIT, bool ALLOUT>
-__global__ void __launch_bounds__(kMX * kMY, IFE_MARCH_MINB)
+__global__ void __launch_bounds__(kMX * kMY, HIST ? IFE_MARCH_MINB_HIST : IFE_MARCH_MINB)
 features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_constant__ FeatArgs A,
                       const int zchunk) {
   constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
   constexpr int NT = kMX * kMY;
   __shared__ float plane[4][kMPlane];   // ring: plane pz+2 lands while plane pz is consumed
   extern __shared__ unsigned char feat_smem[];
-  float* s_edges = reinterpret_cast<float*>(feat_smem);
-  uint32_t* s_counts = reinterpret_cast<uint32_t*>(s_edges + NFEAT * A.hist.n_edges);
+  // Histogram sink.  Shared-memory atomics run at about one lane per clock per SM, far too
+  // slow for eight inserts per voxel, so there are none: every thread owns a private column of
+  // 8-bit counters, four to a word, word q of thread t at s_priv[q*NT + t] (a warp's 32 lanes
+  // always hit 32 different banks), an insert is a plain load/add/store, and a thread sees at
+  // most zchunk <= 255 voxels, so a counter cannot overflow.  Columns are summed once per block.
+  float* s_edges = reinterpret_cast<float*>(feat_smem);          // rows padded with +inf to ep = 2^k
+  const int ep = hist_edge_pitch(A.hist.n_edges);
+  unsigned* s_priv = reinterpret_cast<unsigned*>(s_edges + NFEAT * ep);
   const int nb = A.hist.n_edges + 1;
+  const int nbq = (nb + 3) / 4;                  // words per feature in a private column
+  const int nq = NFEAT * nbq;                    // (features never share a word)
   const int tid = threadIdx.y * kMX + threadIdx.x;
   if (HIST) {
-    for (int i = tid; i < NFEAT * A.hist.n_edges; i += NT) s_edges[i] = A.hist.edges[i];
-    for (int i = tid; i < NFEAT * nb; i += NT) s_counts[i] = 0u;
+    for (int i = tid; i < NFEAT * ep; i += NT) {
+      const int k = i / ep, j = i - k * ep;
+      s_edges[i] = j < A.hist.n_edges ? A.hist.edges[k * A.hist.n_edges + j] : __int_as_float(0x7f800000);
+    }
+    for (int i = tid; i < nq * NT; i += NT) s_priv[i] = 0u;
   }
 
   const int nx = A.nx, ny = A.ny;
@@ -231,12 +252,37 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
             if (ALLOUT || A.out[k]) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = 0.0f;
         }
       }
-      if (HIST) {
+      if (HIST && C.inside) {
+        // eight independent searches, then eight loads, then eight stores: the words are
+        // distinct by construction, so nothing here waits on anything but its own feature
+        int bin[NFEAT];
+        if (ep == 64) {
+          // step-major order: the eight searches advance together, so the eight loads of a
+          // step are in flight at once instead of 48 dependent loads back to back
+          const float* p[NFEAT];
 #pragma unroll
-        for (int k = 0; k < NFEAT; ++k) {
-          const int bin = C.inside ? dense_bin(s_edges + k * A.hist.n_edges, A.hist.n_edges, f[k]) : 0;
-          hist_add(s_counts + k * nb, bin, C.inside);
+          for (int k = 0; k < NFEAT; ++k) p[k] = s_edges + k * 64;
+#pragma unroll
+          for (int step = 32; step >= 1; step >>= 1) {
+            float ev[NFEAT];
+#pragma unroll
+            for (int k = 0; k < NFEAT; ++k) ev[k] = p[k][step - 1];
+#pragma unroll
+            for (int k = 0; k < NFEAT; ++k)
+              if (ev[k] < f[k]) p[k] += step;
+          }
+#pragma unroll
+          for (int k = 0; k < NFEAT; ++k) bin[k] = (int)(p[k] - (s_edges + k * 64));
+        } else {
+#pragma unroll
+          for (int k = 0; k < NFEAT; ++k) bin[k] = dense_bin_padded_rt(s_edges + k * ep, ep, f[k]);
         }
+        unsigned wv[NFEAT];
+#pragma unroll
+        for (int k = 0; k < NFEAT; ++k) wv[k] = s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid];
+#pragma unroll
+        for (int k = 0; k < NFEAT; ++k)
+          s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid] = wv[k] + (1u << ((bin[k] & 3) * 8));
       }
       po += psz;
     }
@@ -255,9 +301,15 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
 
   if (HIST) {
     __syncthreads();
+    // thread i sums counter row i over the NT columns
     for (int i = tid; i < NFEAT * nb; i += NT) {
-      const uint32_t c = s_counts[i];
-      if (c) atomicAdd(A.hist.counts + i, c);
+      const int k = i / nb, bn = i - k * nb;
+      const unsigned* w = s_priv + (k * nbq + (bn >> 2)) * NT;
+      const unsigned sh = (bn & 3) * 8;
+      unsigned total = 0;
+#pragma unroll 8
+      for (int j = 0; j < NT; ++j) total += (w[(j + tid) & (NT - 1)] >> sh) & 0xffu;
+      if (total) atomicAdd(A.hist.counts + i, total);
     }
   }
 }

@@ -331,9 +331,13 @@ void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream
   bool all = true;
   for (int k = 0; k < NFEAT; ++k) all = all && A.out[k] != nullptr;
   if (zchunk > 0) {   // z-marching kernel (everything but ROI-list histograms)
-    if (all && unit) features_march_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A, zchunk);
-    else if (unit) features_march_kernel<MODE, HIST, true, false><<<grid, block, smem, st>>>(S, A, zchunk);
-    else features_march_kernel<MODE, HIST, false, false><<<grid, block, smem, st>>>(S, A, zchunk);
+    auto go = [&](void (*kern)(StencilCoef, FeatArgs, int)) {
+      if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, block, smem, st>>>(S, A, zchunk);
+    };
+    if (all && unit) go(features_march_kernel<MODE, HIST, true, true>);
+    else if (unit) go(features_march_kernel<MODE, HIST, true, false>);
+    else go(features_march_kernel<MODE, HIST, false, false>);
     return;
   }
   if (all && unit) features_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A);
@@ -364,10 +368,25 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
     grid.z = (nzo + zchunk - 1) / zchunk;
   }
   if (grid.y > 65535 || grid.z > 65535) return fail(ctx, IFE_E_INVALID, "volume too large for the launch grid");
-  const size_t smem =
-      hist ? (size_t)nfeat * (A.hist.n_edges * sizeof(float) + (A.hist.n_edges + 1) * sizeof(uint32_t))
-           : 0;
-  if (smem > 30 * 1024)
+  // brick kernel: edge rows as given + uint32 counters; march kernel: rows padded to a power
+  // of two + one private 8-bit counter column per thread (falls back to the brick kernel when
+  // that does not fit)
+  size_t smem = 0;
+  if (hist && zchunk > 0) {
+    smem = (size_t)nfeat * ((size_t)hist_edge_pitch(A.hist.n_edges) * sizeof(float) +
+                            (size_t)((A.hist.n_edges + 4) / 4) * 4 * (kMX * kMY));
+    if (smem > 96 * 1024) {
+      zchunk = 0;
+      block = dim3(kTX, kTY, 1);
+      grid = dim3((A.nx + kTX - 1) / kTX, (A.ny + kTY - 1) / kTY, (nzo + kTZ - 1) / kTZ);
+    } else if (zchunk > 255) {
+      zchunk = 255;    // 8-bit private counters: a thread must not see more than 255 voxels
+      grid.z = (nzo + zchunk - 1) / zchunk;
+    }
+  }
+  if (hist && zchunk == 0)
+    smem = (size_t)nfeat * (A.hist.n_edges * sizeof(float) + (A.hist.n_edges + 1) * sizeof(uint32_t));
+  if (zchunk == 0 && smem > 30 * 1024)
     return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d) for shared memory", A.hist.n_edges);
   cudaStream_t st = ctx->stream();
   ProfScope prof(ctx, mode == 2 ? K_OTHER : K_FEATURES);
