@@ -69,6 +69,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
   constexpr int NT = kMX * kMY;
   __shared__ float plane[4][kMPlane];   // ring: plane pz+2 lands while plane pz is consumed
+  __shared__ __align__(16) unsigned char s_mask[4][kMX * kMY];   // the mask bytes of the same planes
   extern __shared__ unsigned char feat_smem[];
   // Histogram sink.  Shared-memory atomics run at about one lane per clock per SM, far too
   // slow for eight inserts per voxel, so there are none: every thread owns a private column of
@@ -106,13 +107,21 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
   const bool in_xy = x < nx && y < ny;
   const bool has_mask = A.mask_u8 != nullptr;
+  // 4-byte aligned mask rows travel with cp.async like the image (threads 0 .. 8*kMY-1 copy four
+  // bytes each); anything else is fetched per voxel into a register two steps ahead
+  const bool mask_async = has_mask && (nx & 3) == 0 && (reinterpret_cast<size_t>(A.mask_u8) & 3) == 0;
+  const bool mask_copier = mask_async && tid < 8 * kMY;
   // running pointers: plane `pz+1` of the two staged elements and of this voxel's mask byte
   const float* p0 = A.vol + psz * zlo + (size_t)min(max(x0 - 1 + e0c, 0), nx - 1) +
                     (size_t)nx * (size_t)min(max(y0 - 1 + e0r, 0), ny - 1);
   const float* p1 = A.vol + psz * zlo + (size_t)min(max(x0 - 1 + e1c, 0), nx - 1) +
                     (size_t)nx * (size_t)min(max(y0 - 1 + e1r, 0), ny - 1);
-  const uint8_t* pm = (has_mask ? A.mask_u8 : reinterpret_cast<const uint8_t*>(A.vol)) + psz * zlo +
-                      (in_xy ? (size_t)x + (size_t)nx * (size_t)y : 0);
+  const uint8_t* pm = (has_mask ? A.mask_u8 : reinterpret_cast<const uint8_t*>(A.vol)) + psz * zlo;
+  if (mask_async) {
+    if (mask_copier) pm += (size_t)nx * (size_t)min(y0 + (tid >> 3), ny - 1) + (size_t)min(x0 + 4 * (tid & 7), nx - 4);
+  } else {
+    pm += in_xy ? (size_t)x + (size_t)nx * (size_t)y : 0;
+  }
   // output pointer of plane 0 of this voxel; the other planes are uniform byte offsets away
   const size_t o_first = psz * (size_t)(zs - A.zb0) + (size_t)nx * (size_t)y + (size_t)x;
   int first_out = 0;
@@ -140,6 +149,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   auto issue = [&](int slot) {
     cp_async4(&plane[slot][tid], p0);
     if (has1) cp_async4(&plane[slot][e1], p1);
+    if (mask_copier) cp_async4(&s_mask[slot][4 * tid], pm);
     cp_async_commit();
   };
   PlaneTerms T0, T1, T2;
@@ -151,18 +161,19 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   issue(0);                                  // plane zs-1
   advance();
   issue(1);                                  // plane zs; T0 is N at step zs
-  if (has_mask) T0.mraw = __ldg(pm);
+  if (has_mask && !mask_async) T0.mraw = __ldg(pm);
   advance();
 
   auto step = [&](const int pz, const PlaneTerms& P, PlaneTerms& C, PlaneTerms& N) {
     issue((pz - zs + 3) & 3);                // plane pz+2; C is N at step pz+2
-    if (has_mask) C.mraw = __ldg(pm);
+    if (has_mask && !mask_async) C.mraw = __ldg(pm);
     advance();
-    // mask of plane pz: false for the two feeder planes and outside the image
-    N.inside = in_xy && pz >= zs && pz < ze && (!has_mask || opaque_u32(N.mraw) != 0u);
     cp_async_wait<2>();
     __syncthreads();
     const float* pl = plane[(pz - zs + 1) & 3];
+    // mask of plane pz: false for the two feeder planes and outside the image
+    const unsigned mbyte = mask_async ? (unsigned)s_mask[(pz - zs + 1) & 3][tid] : opaque_u32(N.mraw);
+    N.inside = in_xy && pz >= zs && pz < ze && (!has_mask || mbyte != 0u);
 
     // ---- in-plane terms of plane pz ----
     const float c000 = pl[lc];
