@@ -36,7 +36,6 @@ with open(out_md, "w") as f:
             f.write("| %s | %s | %s |\n" % (label, units[ix[key]], " | ".join(d[ix[key]][:12] for d in data)))
 print(open(out_md).read())
 if len(sys.argv) > 3:
-    kind = {"gauss_pass_x": "gauss_pass_x", "features_kernel": "features_fused"}
     traffic = {}
     for n, d in zip(names, data):
         def val(k):
@@ -46,7 +45,7 @@ if len(sys.argv) > 3:
         b = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
         if "gauss_pass_x" in n:
             traffic["gauss_pass_x"] = b
-        elif "features_kernel" in n:
+        elif "features_kernel" in n or "features_march_kernel" in n:
             traffic["features_fused"] = b
         elif "gauss_pass_strided" in n:
             traffic["gauss_pass_y" if "gauss_pass_z" in traffic else "gauss_pass_z"] = b
