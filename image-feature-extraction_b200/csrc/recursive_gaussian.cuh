@@ -552,6 +552,46 @@ __device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, IN
   cp_async_commit();
 }
 
+// Interior chunks of fully populated warps: every plane of the chunk exists and every lane's
+// group of lines is valid, so the copies need no predicates and their addresses are one
+// per-lane base pointer plus warp-uniform plane offsets.
+template <int NF, int INMODE, int L, bool CK>
+__device__ __forceinline__ void stage_issue_fast(const PassArgs& A, AsyncStage<NF, INMODE, L, CK>& S, int t,
+                                                 size_t wbase, int kc, int row_first) {
+  constexpr int ROWS = L + 3;
+  const int lane = t & 31, wcol = t & ~31;
+  const size_t st = (size_t)A.stride;
+  const size_t p0 = wbase + (size_t)(kc * L - 3) * st;   // plane of row 0
+  {
+    const int q = lane >> 3, c = lane & 7;
+    const float* g0 = A.in0 + p0 + (size_t)q * st + 4 * c;
+    const float* g1 = reinterpret_cast<const float*>(A.in1) + p0 + (size_t)q * st + 4 * c;
+    float* s0 = &S.f0[q][wcol + 4 * c];
+    float* s1 = &S.f1[NF == 2 ? q : 0][wcol + 4 * c];
+#pragma unroll
+    for (int m = 0; m < (ROWS + 3) / 4; ++m) {
+      if (4 * m + 3 < row_first) continue;                       // uniform: rows 0..2 only in phase B
+      const bool on = (4 * m + 3 < ROWS || 4 * m + q < ROWS) && 4 * m + q >= row_first;
+      if (on) {
+        cp_async16(s0 + 4 * m * kAsyncThreads, g0 + (size_t)(4 * m) * st);
+        if (NF == 2 && INMODE != IN_IMG_U8) cp_async16(s1 + 4 * m * kAsyncThreads, g1 + (size_t)(4 * m) * st);
+      }
+    }
+  }
+  if (NF == 2 && INMODE == IN_IMG_U8) {
+    const int q = lane >> 1, h = lane & 1;
+    uint8_t* m8 = reinterpret_cast<uint8_t*>(&S.f1[0][0]);
+    const uint8_t* g = reinterpret_cast<const uint8_t*>(A.in1) + p0 + (size_t)q * st + 16 * h;
+#pragma unroll
+    for (int m = 0; m < (ROWS + 15) / 16; ++m) {
+      const int r = 16 * m + q;
+      if (r < ROWS && r >= row_first)
+        cp_async16(m8 + r * kAsyncThreads + wcol + 16 * h, g + (size_t)(16 * m) * st);
+    }
+  }
+  cp_async_commit();
+}
+
 // MASKMODE (DIVIDE only): 0 = no output mask, 1 = uint8 mask, 2 = float mask
 // YBS: the replayed causal values live in shared memory and checkpoints are prefetched into
 // registers instead of stage slots; with STAGES = 2 that is 70 KB per CTA and < 170
@@ -585,15 +625,24 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
   const int kA = min(n_chunks, (A.out_hi + L - 1) / L);
   const int k_lo = max(0, A.out_lo) / L;
 
+  // copies of chunk kc into a stage: predicate-free for interior chunks of full warps
+  const bool warp_full = wline + 32 <= A.n_lines;
+  auto issue = [&](Stage& S, int kc, int row_first, bool with_ckpt) {
+    if (YBS && warp_full && kc * L - 3 + row_first >= 0 && kc * L + L <= n)
+      stage_issue_fast<NF, INMODE, L, !YBS>(A, S, t, wbase, kc, row_first);
+    else
+      stage_issue<NF, INMODE, L, !YBS>(A, S, t, wbase, wline, line, active, kc, row_first, with_ckpt);
+  };
+
   // ---- phase A: causal sweep, checkpoint at every chunk start ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < kA) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, s, 3, false);
+    if (s < kA) issue(stages[s], s, 3, false);
     else cp_async_commit();
   }
   for (int k = 0; k < kA; ++k) {
     const int kn = k + STAGES - 1;
-    if (kn < kA) stage_issue<NF, INMODE, L, !YBS>(A, stages[kn % STAGES], t, wbase, wline, line, active, kn, 3, false);
+    if (kn < kA) issue(stages[kn % STAGES], kn, 3, false);
     else cp_async_commit();
     cp_async_wait<STAGES - 1>();
     __syncwarp();
@@ -647,7 +696,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     const int kc = n_chunks - 1 - s;
-    if (s < nB) stage_issue<NF, INMODE, L, !YBS>(A, stages[s], t, wbase, wline, line, active, kc, kc < kA ? 0 : 3, kc < kA);
+    if (s < nB) issue(stages[s], kc, kc < kA ? 0 : 3, kc < kA);
     else cp_async_commit();
   }
   for (int q = 0; q < nB; ++q) {
@@ -655,7 +704,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     const int qn = q + STAGES - 1;
     if (qn < nB) {
       const int kc = n_chunks - 1 - qn;
-      stage_issue<NF, INMODE, L, !YBS>(A, stages[qn % STAGES], t, wbase, wline, line, active, kc, kc < kA ? 0 : 3, kc < kA);
+      issue(stages[qn % STAGES], kc, kc < kA ? 0 : 3, kc < kA);
     } else {
       cp_async_commit();
     }

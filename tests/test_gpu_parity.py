@@ -264,6 +264,23 @@ def test_emphysema_histograms_whole_mask_and_rois(ctx, oracle):
     assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).sum() <= 2
 
 
+def test_histograms_many_edges_take_the_atomic_kernel(ctx):
+    """200 edges per row do not fit the private-counter columns of the z-march kernel: the call
+    falls back to the brick kernel (shared-memory atomics) and must give the same counts as
+    binning the feature volumes with searchsorted."""
+    shape = (20, 24, 36)
+    img = synth.ct_like(shape, seed=21, n_blobs=4)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    feats = ctx.emphysema_features(img, mask, [1.2])[0]
+    inside = mask != 0
+    for n_edges in (200, 63, 64, 3):
+        edges = np.stack([synth.equalized_edges(feats[k][inside], n_edges) for k in range(8)])
+        counts = ctx.emphysema_histograms(img, mask, [1.2], edges)[0]
+        for k in range(8):
+            ref = np.bincount(np.searchsorted(edges[k], feats[k][inside], side="left"), minlength=n_edges + 1)
+            assert np.array_equal(counts[k], ref), (n_edges, k)
+
+
 def test_histograms_batch_equals_one_call_per_scan(ctx):
     shape = (24, 32, 40)
     sigmas = [0.6, 1.2]
