@@ -521,6 +521,25 @@ def _main(out_stream):
                "h2d_bytes_per_step": int(h_img.numel() * 4 + h_mask.numel()), "d2h_bytes_per_step": int(d2h),
                "api": "ife_cuda_emphysema_%s(..., IFE_MEM_HOST) with pinned host buffers" % ("histograms" if hist else "features")}
 
+        if hist:
+            # BASELINE.json configs[4] on this GPU: a batch of host-resident scans through
+            # ife_cuda_emphysema_histograms_batch (upload of scan i+1 behind the kernels of scan i)
+            nb = 4
+            imgs = [h_img.numpy()] * nb          # the same pinned scan nb times: identical traffic
+            masks = [h_mask.numpy()] * nb
+            rois_b = None if rois is None else np.stack([rois] * nb)
+            ctx.emphysema_histograms_batch(imgs, masks, SIGMAS, edges, rois_b)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.emphysema_histograms_batch(imgs, masks, SIGMAS, edges, rois_b)
+            dtb = (time.perf_counter() - t0) / nb
+            if dist:
+                t = torch.tensor([dtb], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtb = float(t.item())
+            e2e["batch"] = {"value": world * units / dtb / 1e9, "unit": "Gvoxel/s", "ms_per_scan": dtb * 1e3,
+                            "scans_per_call": nb, "api": "ife_cuda_emphysema_histograms_batch (host scans, uploads overlapped)"}
+
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, parity = cpu_baseline(torch, img, mask, ctx, args.arith)

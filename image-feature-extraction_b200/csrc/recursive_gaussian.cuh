@@ -32,6 +32,9 @@
 #include <cuda_runtime.h>
 
 #include "cp_async.cuh"
+#ifndef IFE_CACHE_HINTS
+#define IFE_CACHE_HINTS 0
+#endif
 #include "fdiv.cuh"
 
 namespace ife {
@@ -557,7 +560,8 @@ __device__ __forceinline__ void stage_issue(const PassArgs& A, AsyncStage<NF, IN
 // per-lane base pointer plus warp-uniform plane offsets.
 template <int NF, int INMODE, int L, bool CK>
 __device__ __forceinline__ void stage_issue_fast(const PassArgs& A, AsyncStage<NF, INMODE, L, CK>& S, int t,
-                                                 size_t wbase, int kc, int row_first) {
+                                                 size_t wbase, int kc, int row_first, bool last_use,
+                                                 unsigned long long pol) {
   constexpr int ROWS = L + 3;
   const int lane = t & 31, wcol = t & ~31;
   const size_t st = (size_t)A.stride;
@@ -573,8 +577,13 @@ __device__ __forceinline__ void stage_issue_fast(const PassArgs& A, AsyncStage<N
       if (4 * m + 3 < row_first) continue;                       // uniform: rows 0..2 only in phase B
       const bool on = (4 * m + 3 < ROWS || 4 * m + q < ROWS) && 4 * m + q >= row_first;
       if (on) {
-        cp_async16(s0 + 4 * m * kAsyncThreads, g0 + (size_t)(4 * m) * st);
-        if (NF == 2 && INMODE != IN_IMG_U8) cp_async16(s1 + 4 * m * kAsyncThreads, g1 + (size_t)(4 * m) * st);
+        if (IFE_CACHE_HINTS && last_use) {
+          cp_async16_hint(s0 + 4 * m * kAsyncThreads, g0 + (size_t)(4 * m) * st, pol);
+          if (NF == 2 && INMODE != IN_IMG_U8) cp_async16_hint(s1 + 4 * m * kAsyncThreads, g1 + (size_t)(4 * m) * st, pol);
+        } else {
+          cp_async16(s0 + 4 * m * kAsyncThreads, g0 + (size_t)(4 * m) * st);
+          if (NF == 2 && INMODE != IN_IMG_U8) cp_async16(s1 + 4 * m * kAsyncThreads, g1 + (size_t)(4 * m) * st);
+        }
       }
     }
   }
@@ -627,9 +636,10 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 
   // copies of chunk kc into a stage: predicate-free for interior chunks of full warps
   const bool warp_full = wline + 32 <= A.n_lines;
+  const unsigned long long pol = l2_evict_first_policy();
   auto issue = [&](Stage& S, int kc, int row_first, bool with_ckpt) {
     if (YBS && warp_full && kc * L - 3 + row_first >= 0 && kc * L + L <= n)
-      stage_issue_fast<NF, INMODE, L, !YBS>(A, S, t, wbase, kc, row_first);
+      stage_issue_fast<NF, INMODE, L, !YBS>(A, S, t, wbase, kc, row_first, with_ckpt, pol);
     else
       stage_issue<NF, INMODE, L, !YBS>(A, S, t, wbase, wline, line, active, kc, row_first, with_ckpt);
   };
@@ -721,7 +731,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 #pragma unroll
         for (int f = 0; f < NF; ++f)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ckn[f][kk] = A.ckpt[ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)];
+          for (int kk = 0; kk < 4; ++kk) ckn[f][kk] = IFE_CACHE_HINTS ? __ldcs(A.ckpt + ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)) : A.ckpt[ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)];
       }
       __syncwarp();
       continue;
@@ -756,7 +766,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 #pragma unroll
       for (int f = 0; f < NF; ++f)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) ckn[f][kk] = A.ckpt[ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)];
+        for (int kk = 0; kk < 4; ++kk) ckn[f][kk] = IFE_CACHE_HINTS ? __ldcs(A.ckpt + ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)) : A.ckpt[ckpt_index<NF>(k - 1, f, kk, A.n_lines, line)];
     }
     const size_t obase = base + (size_t)i0 * st;
     auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
@@ -767,11 +777,11 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
         if (active) {
           if (MASKMODE == 1) qv = __ldg(A.mask_u8 + idx) != 0 ? qv : 0.0f;
           if (MASKMODE == 2) qv = __ldg(A.mask_f32 + idx) != 0.0f ? qv : 0.0f;
-          A.out0[idx] = qv;
+          if (IFE_CACHE_HINTS) __stcs(A.out0 + idx, qv); else A.out0[idx] = qv;
         }
       } else if (active) {
-        A.out0[idx] = o[0];
-        if (NF == 2) A.out1[idx] = o[NF - 1];
+        if (IFE_CACHE_HINTS) { __stcs(A.out0 + idx, o[0]); if (NF == 2) __stcs(A.out1 + idx, o[NF - 1]); }
+        else { A.out0[idx] = o[0]; if (NF == 2) A.out1[idx] = o[NF - 1]; }
       }
     };
     if (YBS) {
