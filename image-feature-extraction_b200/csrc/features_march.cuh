@@ -134,6 +134,8 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   for (int k = 0; k < 8; ++k)
     dk[k] = (k < NFEAT && A.out[k]) ? (long long)(A.out[k] - A.out[first_out]) : 0;
   const int lc = (threadIdx.y + 1) * kMPX + threadIdx.x + 1;  // centre in the padded plane
+  const size_t vox_pk = (size_t)nx * (size_t)y + (size_t)x;    // packed-bin sink: voxel offset in a plane
+  size_t pkz = psz * (size_t)(zs - A.zb0);                    //   and the running plane offset
 
   // software pipeline, one plane per step.  Plane pz+2 is copied global -> shared with
   // cp.async (two steps of work hide the HBM latency, no registers held), its mask byte
@@ -288,13 +290,23 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
 #pragma unroll
           for (int k = 0; k < NFEAT; ++k) bin[k] = dense_bin_padded_rt(s_edges + k * ep, ep, f[k]);
         }
-        unsigned wv[NFEAT];
+        if (A.hist.packed) {
+          unsigned long long w = 0;
 #pragma unroll
-        for (int k = 0; k < NFEAT; ++k) wv[k] = s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid];
+          for (int k = 0; k < NFEAT; ++k) w |= (unsigned long long)(unsigned)bin[k] << (8 * k);
+          A.hist.packed[pkz + vox_pk] = w;
+        } else {
+          unsigned wv[NFEAT];
 #pragma unroll
-        for (int k = 0; k < NFEAT; ++k)
-          s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid] = wv[k] + (1u << ((bin[k] & 3) * 8));
+          for (int k = 0; k < NFEAT; ++k) wv[k] = s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid];
+#pragma unroll
+          for (int k = 0; k < NFEAT; ++k)
+            s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid] = wv[k] + (1u << ((bin[k] & 3) * 8));
+        }
+      } else if (HIST && A.hist.packed && in_xy) {
+        A.hist.packed[pkz + vox_pk] = ~0ull;              // outside the mask
       }
+      if (HIST) pkz += psz;
       po += psz;
     }
   };

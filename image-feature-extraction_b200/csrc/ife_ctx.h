@@ -26,10 +26,11 @@ struct Workspace {
   DeviceBuffer in_img, in_mask; // staging for IFE_MEM_HOST inputs
   DeviceBuffer out[2];          // staging for IFE_MEM_HOST outputs (double-buffered per scale)
   DeviceBuffer edges, rois, counts;
+  DeviceBuffer packed;          // eight bin indices per voxel (many-ROI histogram path)
   DeviceBuffer slab_img, slab_mask;  // slab + halo planes (multi-GPU)
   void release_all() {
     DeviceBuffer* all[] = {&a0, &a1, &b0, &b1, &blur, &ckpt, &in_img, &in_mask, &out[0], &out[1],
-                           &edges, &rois, &counts, &slab_img, &slab_mask};
+                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask};
     for (DeviceBuffer* b : all) b->release();
   }
 };

@@ -345,6 +345,16 @@ void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream
   else features_kernel<MODE, HIST, false, false><<<grid, block, smem, st>>>(S, A);
 }
 
+// ROI lists longer than this take the packed-bin path (one block per ROI)
+constexpr int kManyRois = 192;
+
+// shared memory of the z-march kernel's histogram sink: padded edge rows + private counter columns
+inline size_t march_hist_smem(int nfeat, int n_edges) {
+  return (size_t)nfeat * ((size_t)hist_edge_pitch(n_edges) * sizeof(float) +
+                          (size_t)((n_edges + 4) / 4) * 4 * (kMX * kMY));
+}
+inline bool march_hist_fits(int nfeat, int n_edges) { return march_hist_smem(nfeat, n_edges) <= 96 * 1024; }
+
 int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const FeatArgs& A,
                     bool unit_spacing) {
   const bool hist = A.hist.edges != nullptr;
@@ -373,9 +383,8 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
   // that does not fit)
   size_t smem = 0;
   if (hist && zchunk > 0) {
-    smem = (size_t)nfeat * ((size_t)hist_edge_pitch(A.hist.n_edges) * sizeof(float) +
-                            (size_t)((A.hist.n_edges + 4) / 4) * 4 * (kMX * kMY));
-    if (smem > 96 * 1024) {
+    smem = march_hist_smem(nfeat, A.hist.n_edges);
+    if (!march_hist_fits(nfeat, A.hist.n_edges)) {
       zchunk = 0;
       block = dim3(kTX, kTY, 1);
       grid = dim3((A.nx + kTX - 1) / kTX, (A.ny + kTY - 1) / kTY, (nzo + kTZ - 1) / kTZ);
@@ -780,6 +789,12 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
   }
   IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), ctx->stream()));
 
+  // Many ROIs (MakeBagDense, large MakeBag runs): the per-voxel search through the ROI list of
+  // the brick kernel does not scale, so the fused kernel leaves packed bin indices and one
+  // block per ROI counts its box (roi_hist_packed_kernel).
+  const bool many_rois = n_roi > kManyRois && n_edges <= 253 && march_hist_fits(8, n_edges) &&
+                         (long long)nx * ny < (1LL << 28);
+  if (many_rois) IFE_TRY(ctx->ws.packed.reserve(ctx, n * sizeof(unsigned long long)));
   const StencilCoef S = make_stencil_coef(spacing);
   for (int s = 0; s < n_sigma; ++s) {
     float* blur = (float*)ctx->ws.blur.ptr;
@@ -791,9 +806,20 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
     A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
     A.hist.edges = (const float*)ctx->ws.edges.ptr + (size_t)s * 8 * n_edges;
     A.hist.counts = d_counts + (size_t)s * 8 * nb;
-    A.hist.rois = d_rois; A.hist.n_roi = n_roi; A.hist.n_edges = n_edges;
+    A.hist.n_edges = n_edges;
     A.hist.stride_roi = (long long)rows * nb;
-    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+    if (many_rois) {
+      A.hist.packed = (unsigned long long*)ctx->ws.packed.ptr;
+      IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+      ProfScope prof(ctx, K_OTHER);
+      roi_hist_packed_kernel<<<(unsigned)n_roi, 256, (size_t)8 * nb * sizeof(uint32_t), ctx->stream()>>>(
+          A.hist.packed, nx, ny, d_rois, nb, A.hist.counts, A.hist.stride_roi);
+      ctx->launches++;
+      IFE_CUDA_TRY(ctx, cudaGetLastError());
+    } else {
+      A.hist.rois = d_rois; A.hist.n_roi = n_roi;
+      IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+    }
   }
   if (mem == IFE_MEM_HOST) {
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, n_counts * sizeof(uint32_t),

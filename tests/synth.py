@@ -68,6 +68,20 @@ def random_rois(mask, n, size, seed=7):
     return np.array([[x - sx // 2, y - sy // 2, z - sz // 2, sx, sy, sz] for z, y, x in pick], np.int32)
 
 
+def dense_rois(mask, size):
+    """DenseROIGenerator (include/ife/ROI/DenseROIGenerator.hxx:22-45): one box of `size` per
+    non-zero mask voxel, start = index - size/2, kept when it lies inside the image; raster
+    order (x fastest)."""
+    nz, ny, nx = mask.shape
+    sx, sy, sz = size
+    out = []
+    for z, y, x in np.argwhere(mask != 0):          # argwhere is z-major, x fastest: ITK order
+        x0, y0, z0 = x - sx // 2, y - sy // 2, z - sz // 2
+        if x0 >= 0 and y0 >= 0 and z0 >= 0 and x0 + sx <= nx and y0 + sy <= ny and z0 + sz <= nz:
+            out.append([x0, y0, z0, sx, sy, sz])
+    return np.array(out, np.int32).reshape(-1, 6)
+
+
 def equalized_edges(samples, n_edges):
     """n_edges equal-frequency edges from samples (strictly increasing where possible)."""
     q = np.quantile(samples.astype(np.float64), (np.arange(n_edges) + 1) / (n_edges + 1.0))

@@ -264,6 +264,32 @@ def test_emphysema_histograms_whole_mask_and_rois(ctx, oracle):
     assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).sum() <= 2
 
 
+def test_many_rois_one_block_per_roi(ctx, oracle):
+    """MakeBagDense semantics: one ROI per in-mask voxel.  More than 192 ROIs switch to packed
+    bin indices + one block per ROI; the counts must equal the oracle's per-ROI insert loop and
+    the small-list path."""
+    shape = (18, 22, 28)
+    sigmas = [0.6, 1.2]
+    img = synth.ct_like(shape, seed=23, n_blobs=5)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    edges = _edges_for(oracle, img, mask, sigmas, 12)
+    rois = synth.dense_rois(mask, (7, 5, 3))
+    assert len(rois) > 400
+    got = ctx.emphysema_histograms(img, mask, sigmas, edges, rois)
+    assert got.shape == (len(rois), 16, 13)
+    small = np.concatenate([ctx.emphysema_histograms(img, mask, sigmas, edges, rois[i:i + 150])
+                            for i in range(0, len(rois), 150)])
+    assert np.array_equal(got, small)
+    feats = np.concatenate([oracle.emphysema_features(img, mask, s, arith=1) for s in sigmas])
+    pick = np.arange(0, len(rois), 7)
+    ref = oracle.features_histograms(feats, mask, edges, rois[pick])
+    assert np.abs(got[pick].astype(np.int64) - ref.astype(np.int64)).sum() <= 4
+    assert np.array_equal(got[pick][:, [0, 1, 8, 9]], ref[:, [0, 1, 8, 9]])     # blur/gradient rows exact
+    # every ROI row sums to the number of in-mask voxels of its box
+    x0, y0, z0, sx, sy, sz = rois[len(rois) // 2]
+    assert np.all(got[len(rois) // 2].sum(1) == (mask[z0:z0 + sz, y0:y0 + sy, x0:x0 + sx] != 0).sum())
+
+
 def test_histograms_many_edges_take_the_atomic_kernel(ctx):
     """200 edges per row do not fit the private-counter columns of the z-march kernel: the call
     falls back to the brick kernel (shared-memory atomics) and must give the same counts as

@@ -27,6 +27,7 @@ def test_host_selftest(tmp_path):
                                            ("FiniteDifference_HessianFeatures", "-i -m -o"),
                                            ("FiniteDifference_GradientFeatures", "-i -m -o"),
                                            ("MakeBag", "-i -m -H -o -s"),
+                                           ("MakeBagDense", "-i -m -H -o -s"),
                                            ("DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures", "-i -o -b -S -s -f")])
 def test_cli_surface(tool, required):
     p = run(tool, "--help")
@@ -137,6 +138,40 @@ def test_makebag_against_oracle(tmp_path, oracle):
     p = run("MakeBag", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d, "-s", "0.6",
             "-r", d + "/rois.txt")
     assert p.returncode == 1 and "Number of histograms must match" in p.stderr
+
+
+@pytest.mark.gpu
+def test_makebagdense_against_oracle(tmp_path, oracle):
+    """tools/MakeBagDense.cxx semantics: one ROI per non-zero voxel of the ROI mask (here label 2
+    of a ROI-mask file; then the image mask itself), written to .ROIInfo in raster order, and one
+    CSV row of frequencies per ROI."""
+    shape = (20, 24, 30)
+    img = synth.ct_like(shape, seed=62, n_blobs=6)
+    lab = synth.lung_mask(shape).astype(np.uint16)
+    m01 = synth.clamp01(lab.astype(np.uint8))
+    d = str(tmp_path)
+    nifti_util.write(d + "/img.nii.gz", img)
+    nifti_util.write(d + "/mask.nii.gz", lab)
+    sigmas = [0.6, 1.2]
+    feats = np.concatenate([oracle.emphysema_features(img, m01, float(np.float32(s)), arith=1) for s in sigmas])
+    edges = np.stack([synth.equalized_edges(feats[k][m01 != 0], 10) for k in range(16)])
+    with open(d + "/hist.txt", "w") as f:
+        for row in edges:
+            f.write(",".join(repr(float(v)) for v in row) + "\n")
+    for tag, roimask, extra in (("lab2", (lab == 2), ["-M", d + "/mask.nii.gz", "-v", "2"]), ("all", m01 != 0, [])):
+        p = run("MakeBagDense", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d,
+                "-s", "0.6", "-s", "1.2", "-x", "7", "-y", "5", "-z", "3", "-p", tag, *extra)
+        assert p.returncode == 0, p.stderr
+        rois = synth.dense_rois(roimask, (7, 5, 3))
+        lines = open("%s/%s.ROIInfo" % (d, tag)).read().strip().splitlines()
+        assert lines == ["[%d, %d, %d][%d, %d, %d]" % tuple(r) for r in rois]
+        bag = np.loadtxt("%s/%s.bag" % (d, tag), delimiter=",", ndmin=2)
+        assert bag.shape == (len(rois), 16 * 11)
+        pick = np.arange(0, len(rois), 11)
+        counts = oracle.features_histograms(feats, m01, edges, rois[pick]).astype(np.float32)
+        with np.errstate(invalid="ignore"):
+            freq = counts / counts.sum(2, keepdims=True)
+        assert np.allclose(bag[pick].reshape(-1, 16, 11), freq, rtol=2e-5, atol=1e-7, equal_nan=True)
 
 
 @pytest.mark.gpu
