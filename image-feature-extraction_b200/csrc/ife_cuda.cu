@@ -950,6 +950,58 @@ int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const f
   return IFE_OK;
 }
 
+int ife_cuda_intensity_roi_histograms(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                      const int dims[3], const float* edges, int n_edges,
+                                      const int* rois, int n_roi, uint32_t* counts, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !mask || !edges || !counts) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  if (n_edges <= 0) return fail(ctx, IFE_E_INVALID, "need at least one histogram edge");
+  if (n_roi < 0 || (n_roi > 0 && !rois)) return fail(ctx, IFE_E_INVALID, "bad ROI list");
+  const double unit[3] = {1.0, 1.0, 1.0};
+  IFE_TRY(check_dims(ctx, dims, unit));
+  if (n_roi == 0) return IFE_OK;
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int nx = dims[0], ny = dims[1], nz = dims[2];
+  const size_t n = (size_t)nx * ny * nz;
+  for (int r = 0; r < n_roi; ++r) {
+    const int* b = rois + 6 * r;
+    if (b[0] < 0 || b[1] < 0 || b[2] < 0 || b[3] <= 0 || b[4] <= 0 || b[5] <= 0 ||
+        b[0] + b[3] > nx || b[1] + b[4] > ny || b[2] + b[5] > nz)
+      return fail(ctx, IFE_E_INVALID, "ROI %d is not inside the image", r);
+  }
+  const size_t smem = n_edges * sizeof(float) + (n_edges + 1) * sizeof(uint32_t);
+  if (smem > 48 * 1024) return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d)", n_edges);
+  const float* d_img;
+  const uint8_t* d_mask;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
+  IFE_TRY(ctx->ws.edges.reserve(ctx, n_edges * sizeof(float)));
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.edges.ptr, edges, n_edges * sizeof(float),
+                                    cudaMemcpyHostToDevice, ctx->stream()));
+  IFE_TRY(ctx->ws.rois.reserve(ctx, (size_t)n_roi * 6 * sizeof(int)));
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.rois.ptr, rois, (size_t)n_roi * 6 * sizeof(int),
+                                    cudaMemcpyHostToDevice, ctx->stream()));
+  const size_t n_counts = (size_t)n_roi * (n_edges + 1);
+  uint32_t* d_counts = counts;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.counts.reserve(ctx, n_counts * sizeof(uint32_t)));
+    d_counts = (uint32_t*)ctx->ws.counts.ptr;
+  }
+  {
+    ProfScope prof(ctx, K_OTHER);
+    roi_intensity_hist_kernel<<<(unsigned)n_roi, 256, smem, ctx->stream()>>>(
+        d_img, d_mask, nx, ny, (const int*)ctx->ws.rois.ptr, (const float*)ctx->ws.edges.ptr, n_edges, d_counts);
+    ctx->launches++;
+    IFE_CUDA_TRY(ctx, cudaGetLastError());
+  }
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, n_counts * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
 int ife_cuda_sort_f32(ife_cuda_ctx* ctx, float* data, size_t n, int mem) {
   if (!ctx) return IFE_E_INVALID;
   if (n == 0) return IFE_OK;

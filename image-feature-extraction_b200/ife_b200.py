@@ -71,6 +71,7 @@ def load_library():
     L.ife_cuda_emphysema_histograms.argtypes = [vp, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp, i]
     L.ife_cuda_emphysema_histograms_batch.argtypes = [vp, i, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp]
     L.ife_cuda_histogram.argtypes = [vp, vp, sz, vp, i, vp, i]
+    L.ife_cuda_intensity_roi_histograms.argtypes = [vp, vp, vp, ip, vp, i, vp, i, vp, i]
     L.ife_cuda_eigen_features_batch.argtypes = [vp, vp, vp, sz, i]
     L.ife_cuda_sort_f32.argtypes = [vp, vp, sz, i]
     L.ife_cuda_comm_unique_id.argtypes = [vp, vp]
@@ -284,6 +285,18 @@ class Context:
         self._check(self.L.ife_cuda_histogram(self.h, _ptr(values) if values.size else None,
                                               values.size, _ptr(edges), edges.size, _ptr(counts),
                                               MEM_HOST))
+        return counts
+
+    def intensity_roi_histograms(self, image, mask, edges, rois):
+        """-> counts (n_roi, n_edges+1): MakeBagOnlyIntensity's per-ROI intensity histograms"""
+        image = np.ascontiguousarray(image, np.float32)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        edges = np.ascontiguousarray(edges, np.float32).ravel()
+        r = np.ascontiguousarray(rois, np.int32).reshape(-1, 6)
+        counts = np.zeros((len(r), edges.size + 1), np.uint32)
+        self._check(self.L.ife_cuda_intensity_roi_histograms(
+            self.h, _ptr(image), _ptr(mask), _i3(_dims_of(image)), _ptr(edges), edges.size,
+            _ptr(r) if len(r) else None, len(r), _ptr(counts), MEM_HOST))
         return counts
 
     def sort(self, values):

@@ -181,6 +181,14 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
 int ife_cuda_histogram(ife_cuda_ctx* ctx, const float* values, size_t n, const float* edges,
                        int n_edges, uint32_t* counts, int mem);
 
+/* tools/MakeBagOnlyIntensity.cxx:352-391: for every ROI box {x0,y0,z0,sx,sy,sz} the
+ * intensities of its in-mask voxels (mask != 0) are inserted into ONE DenseHistogram<float>
+ * with the given edges.  rois: host int[n_roi][6]; edges: host float[n_edges];
+ * counts: uint32[n_roi][n_edges+1] (overwritten), host or device per `mem`, like image / mask. */
+int ife_cuda_intensity_roi_histograms(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                      const int dims[3], const float* edges, int n_edges,
+                                      const int* rois, int n_roi, uint32_t* counts, int mem);
+
 /* Ascending in-place sort of n floats: the `std::sort` of the feature samples in
  * tools/DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx:282-283 (device radix
  * sort; the equal-frequency edge walk of DetermineEdgesForEqualizedHistogram.h then runs

@@ -28,6 +28,7 @@ def test_host_selftest(tmp_path):
                                            ("FiniteDifference_GradientFeatures", "-i -m -o"),
                                            ("MakeBag", "-i -m -H -o -s"),
                                            ("MakeBagDense", "-i -m -H -o -s"),
+                                           ("MakeBagOnlyIntensity", "-i -m -H -o"),
                                            ("DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures", "-i -o -b -S -s -f")])
 def test_cli_surface(tool, required):
     p = run(tool, "--help")
@@ -138,6 +139,41 @@ def test_makebag_against_oracle(tmp_path, oracle):
     p = run("MakeBag", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d, "-s", "0.6",
             "-r", d + "/rois.txt")
     assert p.returncode == 1 and "Number of histograms must match" in p.stderr
+
+
+@pytest.mark.gpu
+def test_makebagonlyintensity(tmp_path, ctx):
+    """tools/MakeBagOnlyIntensity.cxx semantics: one intensity histogram per ROI over its in-mask
+    voxels; exactly one edge row accepted."""
+    shape = (22, 26, 30)
+    img = synth.ct_like(shape, seed=63, n_blobs=6)
+    lab = synth.lung_mask(shape).astype(np.uint16)
+    m01 = synth.clamp01(lab.astype(np.uint8))
+    d = str(tmp_path)
+    nifti_util.write(d + "/img.nii.gz", img)
+    nifti_util.write(d + "/mask.nii.gz", lab)
+    edges = synth.equalized_edges(img[m01 != 0], 14)
+    open(d + "/hist.txt", "w").write(",".join(repr(float(v)) for v in edges) + "\n")
+    rois = synth.random_rois(m01, 6, (9, 7, 5), seed=5)
+    with open(d + "/rois.txt", "w") as f:
+        f.write("header line\n")
+        for r in rois:
+            f.write("[%d, %d, %d][%d, %d, %d]\n" % tuple(r))
+    p = run("MakeBagOnlyIntensity", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/hist.txt", "-o", d,
+            "-r", d + "/rois.txt", "-p", "int")
+    assert p.returncode == 0, p.stderr
+    bag = np.loadtxt(d + "/int.bag", delimiter=",", ndmin=2)
+    assert bag.shape == (6, 15)
+    for j, (x0, y0, z0, sx, sy, sz) in enumerate(rois):
+        box, mb = img[z0:z0 + sz, y0:y0 + sy, x0:x0 + sx], m01[z0:z0 + sz, y0:y0 + sy, x0:x0 + sx] != 0
+        cnt = np.bincount(np.searchsorted(edges, box[mb], side="left"), minlength=15).astype(np.float32)
+        assert np.allclose(bag[j], cnt / np.float32(cnt.sum()), rtol=2e-5, atol=1e-7, equal_nan=True)   # 6 printed digits
+    assert np.array_equal(ctx.intensity_roi_histograms(img, m01, edges, rois).sum(1),
+                          [(m01[z:z + c, y:y + b, x:x + a] != 0).sum() for x, y, z, a, b, c in rois])
+    open(d + "/two.txt", "w").write("0,1\n2,3\n")
+    p = run("MakeBagOnlyIntensity", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-H", d + "/two.txt", "-o", d,
+            "-r", d + "/rois.txt")
+    assert p.returncode == 1 and "Expected exactly one histogram" in p.stderr
 
 
 @pytest.mark.gpu
