@@ -364,6 +364,7 @@ def _main(out_stream):
     ap.add_argument("--rois", type=int, default=0, help="hist workload: bin into N fixed-seed 41^3 ROIs (MakeBag) instead of the whole mask")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-box", action="store_true", help="A/B: smooth the whole volume even where the mask cannot see it")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out_stream)
@@ -389,6 +390,8 @@ def _main(out_stream):
     ctx = ife_b200.Context(local_rank, arith=ife_b200.ARITH_FMA if args.arith == "fma" else ife_b200.ARITH_PLAIN)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
+    if args.no_box:
+        ctx.set_option("support_box", 0)
     if args.workload == "slab":
         return run_slab(args, torch, dist, ctx, stream, dev, world, rank, local_rank, warmup, out_stream)
     nx, ny, nz = DIMS

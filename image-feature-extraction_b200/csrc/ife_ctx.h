@@ -28,9 +28,10 @@ struct Workspace {
   DeviceBuffer edges, rois, counts;
   DeviceBuffer packed;          // eight bin indices per voxel (many-ROI histogram path)
   DeviceBuffer slab_img, slab_mask;  // slab + halo planes (multi-GPU)
+  DeviceBuffer box;             // support box of the output mask: raw extents[6] + box[6] (int)
   void release_all() {
     DeviceBuffer* all[] = {&a0, &a1, &b0, &b1, &blur, &ckpt, &in_img, &in_mask, &out[0], &out[1],
-                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask};
+                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box};
     for (DeviceBuffer* b : all) b->release();
   }
 };
@@ -61,6 +62,7 @@ struct ife_cuda_ctx {
   cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   bool use_async = true;   // cp.async software-pipelined Gaussian passes (option "async_passes")
+  bool use_box = true;     // masked paths smooth only the mask's support box (option "support_box")
   std::string error;
   ife::Workspace ws;
   // optional per-kernel timing (ife_cuda_profile_*): event pairs around every launch

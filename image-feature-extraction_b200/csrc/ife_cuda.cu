@@ -17,6 +17,7 @@
 #include "eigen_features.cuh"
 #include "features_march.cuh"
 #include "recursive_gaussian.cuh"
+#include "support_box.cuh"
 #include "ife_ctx.h"
 
 namespace ife {
@@ -259,7 +260,7 @@ int launch_x(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
 int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool cert_is_u8,
                   float* out0, int nx, int ny, int nzb, int keep0, int keep1,
                   const double spacing[3], double sigma, const uint8_t* outmask_u8,
-                  const float* outmask_f32) {
+                  const float* outmask_f32, const int* d_box = nullptr) {
   if (nx < 4 || ny < 4 || nzb < 4)
     return fail(ctx, IFE_E_TOO_SMALL,
                 "recursive Gaussian needs at least 4 samples per axis (got %d x %d x %d)", nx, ny,
@@ -285,6 +286,9 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   A.n = nzb; A.stride = (long long)nx * ny; A.na = nx * ny > 0 ? nx * ny : 1; A.sb = 0;
   A.out_lo = keep0; A.out_hi = keep1;   // a z-slab's halo planes only carry recursion state
   A.n_lines = (long long)nx * ny;
+  // support box (masked paths): z pass keeps the box's planes, the x pass runs the rows of those
+  // planes, the y pass the columns (x, z) that cross the box and only its y range
+  A.box = d_box; A.box_a = -1; A.box_b = -1; A.box_o = 2; A.box_b_off = 0;
   if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cz, A)));
   else if (cert_is_u8) IFE_TRY((launch_strided<2, IN_IMG_U8, false>(ctx, cz, A)));
   else IFE_TRY((launch_strided<2, IN_IMG_F32, false>(ctx, cz, A)));
@@ -293,8 +297,9 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   const int nzk = keep1 - keep0;
   const size_t koff = (size_t)keep0 * nx * ny;
   A.in0 = a0 + koff; A.in1 = a1 + koff; A.out0 = b0; A.out1 = b1;
-  A.n = nx; A.stride = 1; A.na = 1; A.sb = 0; A.n_lines = (long long)ny * nzk;
+  A.n = nx; A.stride = 1; A.na = d_box ? ny : 1; A.sb = 0; A.n_lines = (long long)ny * nzk;
   A.out_lo = 0; A.out_hi = nx;
+  A.box_a = -1; A.box_b = 2; A.box_o = -1; A.box_b_off = keep0;
   if (nf == 1) IFE_TRY((launch_x<1>(ctx, cx, A)));
   else IFE_TRY((launch_x<2>(ctx, cx, A)));
 
@@ -302,9 +307,47 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   A.in0 = b0; A.in1 = b1; A.out0 = out0; A.out1 = nullptr;
   A.n = ny; A.stride = nx; A.na = nx; A.sb = (long long)nx * ny; A.n_lines = (long long)nx * nzk;
   A.out_lo = 0; A.out_hi = ny;
+  A.box_a = 0; A.box_b = 2; A.box_o = 1; A.box_b_off = keep0;
   A.mask_u8 = outmask_u8; A.mask_f32 = outmask_f32;
   if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cy, A)));
   else IFE_TRY((launch_strided<2, IN_FIELDS, true>(ctx, cy, A)));
+  return IFE_OK;
+}
+
+// Support box of `d_mask` (optionally clipped to the bounding box of an ROI list, host array of
+// n_roi x {x,y,z,sx,sy,sz}) for the masked smoothing paths; *d_box stays null when the option
+// is off or the layout does not allow the 16-byte scan (the passes then run everywhere).
+int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz,
+                        const int* rois, int n_roi, const int** d_box) {
+  *d_box = nullptr;
+  if (!ctx->use_box || !d_mask || nx % 16 != 0 || reinterpret_cast<uintptr_t>(d_mask) % 16 != 0)
+    return IFE_OK;
+  IFE_TRY(ctx->ws.box.reserve(ctx, 12 * sizeof(int)));
+  int* raw = (int*)ctx->ws.box.ptr;
+  int* box = raw + 6;
+  BoxLimits lim;
+  const int n[3] = {nx, ny, nz};
+  for (int d = 0; d < 3; ++d) { lim.lo[d] = 0; lim.hi[d] = n[d]; lim.n[d] = n[d]; }
+  if (n_roi > 0 && rois) {
+    for (int d = 0; d < 3; ++d) { lim.lo[d] = n[d]; lim.hi[d] = 0; }
+    for (int r = 0; r < n_roi; ++r)
+      for (int d = 0; d < 3; ++d) {
+        lim.lo[d] = std::min(lim.lo[d], rois[6 * r + d]);
+        lim.hi[d] = std::max(lim.hi[d], rois[6 * r + d] + rois[6 * r + 3 + d]);
+      }
+  }
+  cudaStream_t st = ctx->stream();
+  IFE_CUDA_TRY(ctx, cudaMemsetAsync(raw, 0, 6 * sizeof(int), st));
+  const long long n_pieces = (long long)nx * ny * nz / 16;
+  const unsigned grid = (unsigned)std::min<long long>((n_pieces + 255) / 256, 8LL * ctx->sm_count);
+  {
+    ProfScope prof(ctx, K_OTHER);
+    mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_pieces, raw);
+  }
+  box_finish_kernel<<<1, 32, 0, st>>>(raw, lim, box);
+  ctx->launches += 2;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  *d_box = box;
   return IFE_OK;
 }
 
@@ -350,8 +393,8 @@ constexpr int kManyRois = 192;
 
 // shared memory of the z-march kernel's histogram sink: padded edge rows + private counter columns
 inline size_t march_hist_smem(int nfeat, int n_edges) {
-  return (size_t)nfeat * ((size_t)hist_edge_pitch(n_edges) * sizeof(float) +
-                          (size_t)((n_edges + 4) / 4) * 4 * (kMX * kMY));
+  return (size_t)nfeat * ((size_t)hist_row_pitch(n_edges) * sizeof(float) +
+                          (size_t)hist_bin_words(n_edges) * 4 * (kMX * kMY));
 }
 inline bool march_hist_fits(int nfeat, int n_edges) { return march_hist_smem(nfeat, n_edges) <= 96 * 1024; }
 
@@ -519,6 +562,7 @@ uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx) { return ctx ? ctx->laun
 int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return IFE_E_INVALID;
   if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
+  if (std::strcmp(name, "support_box") == 0) { ctx->use_box = value != 0; return IFE_OK; }
   return fail(ctx, IFE_E_INVALID, "unknown option '%s'", name);
 }
 
@@ -715,13 +759,15 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
     if (n_sigma > 1) IFE_TRY(ctx->ws.out[1].reserve(ctx, 8 * n * sizeof(float)));
   }
   const StencilCoef S = make_stencil_coef(spacing);
+  const int* d_box;   // all eight outputs are masked: smooth only what in-mask voxels can see
+  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, nullptr, 0, &d_box));
   for (int s = 0; s < n_sigma; ++s) {
     float* blur = (float*)ctx->ws.blur.ptr;
     float* d_out = mem == IFE_MEM_HOST ? (float*)ctx->ws.out[s & 1].ptr : out + (size_t)s * 8 * n;
     if (mem == IFE_MEM_HOST && s >= 2)  // the staging buffer must have been drained
       IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream(), ctx->events[2 + (s & 1)], 0));
     IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                          nullptr, nullptr));
+                          nullptr, nullptr, d_box));
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
     A.vol = blur; A.mask_u8 = d_mask;
@@ -796,10 +842,12 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
                          (long long)nx * ny < (1LL << 28);
   if (many_rois) IFE_TRY(ctx->ws.packed.reserve(ctx, n * sizeof(unsigned long long)));
   const StencilCoef S = make_stencil_coef(spacing);
+  const int* d_box;   // only in-mask voxels (inside some ROI, when there are ROIs) are binned
+  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, rois, n_roi, &d_box));
   for (int s = 0; s < n_sigma; ++s) {
     float* blur = (float*)ctx->ws.blur.ptr;
     IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                          nullptr, nullptr));
+                          nullptr, nullptr, d_box));
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
     A.vol = blur; A.mask_u8 = d_mask;
@@ -892,10 +940,13 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
     const uint8_t* d_mask = (const uint8_t*)mask_slot[k]->ptr;
     uint32_t* d_counts = (uint32_t*)ws.counts.ptr + (size_t)k * n_counts;
     IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), st));
+    const int* d_box;
+    IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr,
+                                n_roi, &d_box));
     for (int s = 0; s < n_sigma; ++s) {
       float* blur = (float*)ws.blur.ptr;
       IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                            nullptr, nullptr));
+                            nullptr, nullptr, d_box));
       FeatArgs A;
       std::memset(&A, 0, sizeof(A));
       A.vol = blur; A.mask_u8 = d_mask;

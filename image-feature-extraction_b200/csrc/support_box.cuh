@@ -1,0 +1,85 @@
+// Support box of the output mask.
+//
+// Every consumer of the smoothed volume on the masked paths -- the fused feature kernel behind
+// ImageToEmphysemaFeaturesFilter (its eight MaskImageFilters,
+// include/ife/Filters/ImageToEmphysemaFeaturesFilter.hxx:44-54) and the histogram loop of
+// tools/MakeBag.cxx:448-457 -- only looks at voxels inside the mask, and the stencils of such a
+// voxel reach one voxel further in every direction.  So the smoothed volume is only needed
+// inside the mask's bounding box grown by one voxel.  The recursion itself has infinite
+// support and must still run along complete lines, but lines that miss the box need not run at
+// all and, along a line, nothing below the box needs the anticausal sweep and nothing above it
+// the causal one (recursive_gaussian.cuh: PassArgs::box).  The box is found on the device and
+// read by the passes from device memory, so no call waits for the host.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ife {
+
+constexpr int kBoxBig = 1 << 30;
+
+// raw[2*d] = max(kBoxBig - min coordinate), raw[2*d+1] = max(coordinate + 1) over the non-zero
+// voxels; all zero (as cudaMemsetAsync leaves it) = no voxel yet.
+// Requires nx % 16 == 0 and a 16-byte aligned mask: a thread tests 16 voxels of one row.
+__global__ void __launch_bounds__(256)
+mask_box_kernel(const uint8_t* __restrict__ mask, int nx, int ny, long long n_pieces, int* __restrict__ raw) {
+  const int ppr = nx >> 4;   // 16-byte pieces per row
+  int xlo = kBoxBig, xhi = 0, ylo = kBoxBig, yhi = 0, zlo = kBoxBig, zhi = 0;
+  const uint4* m16 = reinterpret_cast<const uint4*>(mask);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pieces;
+       p += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(m16 + p);
+    if ((v.x | v.y | v.z | v.w) == 0u) continue;
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    int first = 16, last = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // bit 7 of every non-zero byte
+      const unsigned t = (w[k] | ((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+      if (t) {
+        first = min(first, 4 * k + ((__ffs(t) - 1) >> 3));
+        last = max(last, 4 * k + ((31 - __clz(t)) >> 3));
+      }
+    }
+    const long long row = p / ppr;
+    const int x0 = (int)(p - row * ppr) << 4;
+    const int y = (int)(row % ny), z = (int)(row / ny);
+    xlo = min(xlo, x0 + first); xhi = max(xhi, x0 + last + 1);
+    ylo = min(ylo, y); yhi = max(yhi, y + 1);
+    zlo = min(zlo, z); zhi = max(zhi, z + 1);
+  }
+  const unsigned full = 0xffffffffu;
+  xlo = __reduce_min_sync(full, xlo); xhi = __reduce_max_sync(full, xhi);
+  ylo = __reduce_min_sync(full, ylo); yhi = __reduce_max_sync(full, yhi);
+  zlo = __reduce_min_sync(full, zlo); zhi = __reduce_max_sync(full, zhi);
+  if ((threadIdx.x & 31) == 0 && xhi > 0) {
+    atomicMax(raw + 0, kBoxBig - xlo); atomicMax(raw + 1, xhi);
+    atomicMax(raw + 2, kBoxBig - ylo); atomicMax(raw + 3, yhi);
+    atomicMax(raw + 4, kBoxBig - zlo); atomicMax(raw + 5, zhi);
+  }
+}
+
+struct BoxLimits {
+  int lo[3], hi[3];   // only voxels inside [lo, hi) count (the bounding box of an ROI list)
+  int n[3];
+};
+
+// raw extents -> box[6] = {x0,x1,y0,y1,z0,z1}: clipped to the limits, grown by the stencil
+// reach of one voxel, clipped to the volume; all zero when nothing is wanted
+__global__ void box_finish_kernel(const int* __restrict__ raw, const __grid_constant__ BoxLimits lim,
+                                  int* __restrict__ box) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int lo[3], hi[3];
+  bool empty = false;
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = max(kBoxBig - raw[2 * d], lim.lo[d]);
+    hi[d] = min(raw[2 * d + 1], lim.hi[d]);
+    empty = empty || lo[d] >= hi[d];
+  }
+  for (int d = 0; d < 3; ++d) {
+    box[2 * d] = empty ? 0 : max(lo[d] - 1, 0);
+    box[2 * d + 1] = empty ? 0 : min(hi[d] + 1, lim.n[d]);
+  }
+}
+
+}  // namespace ife

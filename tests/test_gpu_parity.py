@@ -215,6 +215,48 @@ def test_emphysema_features_ragged_and_all_ones_mask(ctx, oracle):
     assert np.all(ctx.emphysema_features(img, none, [1.0]) == 0)
 
 
+def test_support_box_is_invisible(ctx, oracle):
+    """Masked paths smooth only the mask's bounding box grown by the stencil reach (lines that
+    miss it are skipped, the sweeps along a line stop at it).  No result may change: the same
+    call with the option off, and the oracle, give identical outputs; an empty mask and a mask
+    touching the volume corner work too."""
+    shape = (40, 64, 96)                      # nz, ny, nx: every pass takes its pipelined kernel
+    sigmas = [0.6, 2.4]
+    img = synth.ct_like(shape, seed=31, n_blobs=10)
+    zz, yy, xx = np.ogrid[:shape[0], :shape[1], :shape[2]]
+    blob = (((zz - 27) / 6.0) ** 2 + ((yy - 20) / 9.0) ** 2 + ((xx - 70) / 11.0) ** 2 <= 1).astype(np.uint8)
+    corner = np.zeros(shape, np.uint8); corner[:3, :2, :5] = 1; corner[-1, -1, -1] = 1
+    for mask in (blob, corner):
+        out = ctx.emphysema_features(img, mask, sigmas)
+        ctx.set_option("support_box", 0)
+        try:
+            full = ctx.emphysema_features(img, mask, sigmas)
+        finally:
+            ctx.set_option("support_box", 1)
+        assert bits_equal(out, full)
+        assert np.all(out[:, :, mask == 0] == 0)
+    for s, sigma in enumerate(sigmas):        # `out` is the corner mask's result
+        ref = oracle.emphysema_features(img, corner, sigma, arith=1)
+        assert mismatch_report(out[s, :2], ref[:2])[0] == 0
+        assert_eigen_parity(np.moveaxis(out[s, 2:], 0, -1), np.moveaxis(ref[2:], 0, -1), "box sigma=%g" % sigma)
+    assert np.all(ctx.emphysema_features(img, np.zeros(shape, np.uint8), sigmas) == 0)
+    # histograms: the box is also clipped to the ROI list's bounding box
+    edges = _edges_for(oracle, img, blob, sigmas, 12)
+    rois = np.array([[60, 12, 22, 9, 7, 5], [72, 20, 26, 11, 9, 6]], np.int32)   # x,y,z,sx,sy,sz
+    for r in (None, rois):
+        got = ctx.emphysema_histograms(img, blob, sigmas, edges, r)
+        ctx.set_option("support_box", 0)
+        try:
+            full = ctx.emphysema_histograms(img, blob, sigmas, edges, r)
+        finally:
+            ctx.set_option("support_box", 1)
+        assert np.array_equal(got, full)
+    assert got.sum() > 0
+    both = ctx.emphysema_histograms_batch([img, img], [blob, corner], sigmas, edges)
+    assert np.array_equal(both[0], ctx.emphysema_histograms(img, blob, sigmas, edges))
+    assert np.array_equal(both[1], ctx.emphysema_histograms(img, corner, sigmas, edges))
+
+
 # ------------------------------------------------------------------------------ histograms
 def test_histogram_flat_array(ctx, oracle):
     import os
