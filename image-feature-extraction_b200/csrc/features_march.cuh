@@ -37,21 +37,7 @@ __host__ __device__ inline int hist_edge_pitch(int n_edges) {
   int ep = 2;
   while (ep <= n_edges) ep <<= 1;
   return ep;
-}
-// Bank skew of the 64-entry rows.  The lower-bound search probes, at the step of width s,
-// positions s-1 + m*2s; positions 32 apart share a bank, so lanes that took different turns
-// at the first step collide two-way at every later step.  Storing the upper half one float
-// further (slot 32 stays empty) puts the probes of every step in 32 distinct banks.  The
-// search then steps over the gap once (first step += 33) and bins above the gap come out one
-// too high: the private counters simply have one more slot, un-skewed when they are flushed.
-__host__ __device__ inline int hist_row_pitch(int n_edges) {
-  const int ep = hist_edge_pitch(n_edges);
-  return ep == 64 ? 65 : ep;
-}
-// words of packed 8-bit counters per feature in a thread's private column (n_edges + 1 bins
-// and the skew's spare slot)
-__host__ __device__ inline int hist_bin_words(int n_edges) { return (n_edges + 2 + 3) / 4; }
-// the block's (x, y) footprint
+}          // the block's (x, y) footprint
 constexpr int kMPX = kMX + 2, kMPY = kMY + 2;
 constexpr int kMPlane = kMPX * kMPY;      // 340 staged values per plane
 
@@ -92,18 +78,15 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   // most zchunk <= 255 voxels, so a counter cannot overflow.  Columns are summed once per block.
   float* s_edges = reinterpret_cast<float*>(feat_smem);          // rows padded with +inf to ep = 2^k
   const int ep = hist_edge_pitch(A.hist.n_edges);
-  const int erp = hist_row_pitch(A.hist.n_edges);                // 65 (bank-skewed) when ep == 64
-  unsigned* s_priv = reinterpret_cast<unsigned*>(s_edges + NFEAT * erp);
+  unsigned* s_priv = reinterpret_cast<unsigned*>(s_edges + NFEAT * ep);
   const int nb = A.hist.n_edges + 1;
-  const int nbq = hist_bin_words(A.hist.n_edges);   // words per feature in a private column
+  const int nbq = (nb + 3) / 4;                  // words per feature in a private column
   const int nq = NFEAT * nbq;                    // (features never share a word)
   const int tid = threadIdx.y * kMX + threadIdx.x;
   if (HIST) {
-    for (int i = tid; i < NFEAT * erp; i += NT) {
-      const int k = i / erp, jp = i - k * erp;
-      const int j = (ep == 64 && jp >= 32) ? jp - 1 : jp;       // slot 32 of a skewed row is the gap
-      const bool real = j < A.hist.n_edges && !(ep == 64 && jp == 32);
-      s_edges[i] = real ? A.hist.edges[k * A.hist.n_edges + j] : __int_as_float(0x7f800000);
+    for (int i = tid; i < NFEAT * ep; i += NT) {
+      const int k = i / ep, j = i - k * ep;
+      s_edges[i] = j < A.hist.n_edges ? A.hist.edges[k * A.hist.n_edges + j] : __int_as_float(0x7f800000);
     }
     for (int i = tid; i < nq * NT; i += NT) s_priv[i] = 0u;
   }
@@ -291,7 +274,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
           // step are in flight at once instead of 48 dependent loads back to back
           const float* p[NFEAT];
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) p[k] = s_edges + k * 65;
+          for (int k = 0; k < NFEAT; ++k) p[k] = s_edges + k * 64;
 #pragma unroll
           for (int step = 32; step >= 1; step >>= 1) {
             float ev[NFEAT];
@@ -299,10 +282,10 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
             for (int k = 0; k < NFEAT; ++k) ev[k] = p[k][step - 1];
 #pragma unroll
             for (int k = 0; k < NFEAT; ++k)
-              if (ev[k] < f[k]) p[k] += step == 32 ? 33 : step;   // over the gap of the skewed row
+              if (ev[k] < f[k]) p[k] += step;
           }
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) bin[k] = (int)(p[k] - (s_edges + k * 65));   // skewed: +1 above the gap
+          for (int k = 0; k < NFEAT; ++k) bin[k] = (int)(p[k] - (s_edges + k * 64));
         } else {
 #pragma unroll
           for (int k = 0; k < NFEAT; ++k) bin[k] = dense_bin_padded_rt(s_edges + k * ep, ep, f[k]);
@@ -310,10 +293,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
         if (A.hist.packed) {
           unsigned long long w = 0;
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) {
-            const int b = ep == 64 ? bin[k] - (bin[k] > 32 ? 1 : 0) : bin[k];   // true bin index
-            w |= (unsigned long long)(unsigned)b << (8 * k);
-          }
+          for (int k = 0; k < NFEAT; ++k) w |= (unsigned long long)(unsigned)bin[k] << (8 * k);
           A.hist.packed[pkz + vox_pk] = w;
         } else {
           unsigned wv[NFEAT];
@@ -347,9 +327,8 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
     // thread i sums counter row i over the NT columns
     for (int i = tid; i < NFEAT * nb; i += NT) {
       const int k = i / nb, bn = i - k * nb;
-      const int slot = (ep == 64 && bn >= 32) ? bn + 1 : bn;      // bins above the gap sit one slot up
-      const unsigned* w = s_priv + (k * nbq + (slot >> 2)) * NT;
-      const unsigned sh = (slot & 3) * 8;
+      const unsigned* w = s_priv + (k * nbq + (bn >> 2)) * NT;
+      const unsigned sh = (bn & 3) * 8;
       unsigned total = 0;
 #pragma unroll 8
       for (int j = 0; j < NT; ++j) total += (w[(j + tid) & (NT - 1)] >> sh) & 0xffu;

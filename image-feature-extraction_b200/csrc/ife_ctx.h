@@ -28,7 +28,7 @@ struct Workspace {
   DeviceBuffer edges, rois, counts;
   DeviceBuffer packed;          // eight bin indices per voxel (many-ROI histogram path)
   DeviceBuffer slab_img, slab_mask;  // slab + halo planes (multi-GPU)
-  DeviceBuffer box;             // support box of the output mask: raw extents[6] + box[6] (int)
+  DeviceBuffer box;             // raw extents[6] of the output mask (support_box.cuh)
   void release_all() {
     DeviceBuffer* all[] = {&a0, &a1, &b0, &b1, &blur, &ckpt, &in_img, &in_mask, &out[0], &out[1],
                            &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box};
@@ -63,6 +63,7 @@ struct ife_cuda_ctx {
   uint64_t launches = 0;
   bool use_async = true;   // cp.async software-pipelined Gaussian passes (option "async_passes")
   bool use_box = true;     // masked paths smooth only the mask's support box (option "support_box")
+  int* box_host = nullptr; // pinned: the mask extents come back here once per call
   std::string error;
   ife::Workspace ws;
   // optional per-kernel timing (ife_cuda_profile_*): event pairs around every launch

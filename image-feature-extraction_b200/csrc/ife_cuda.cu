@@ -260,13 +260,24 @@ int launch_x(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
 int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool cert_is_u8,
                   float* out0, int nx, int ny, int nzb, int keep0, int keep1,
                   const double spacing[3], double sigma, const uint8_t* outmask_u8,
-                  const float* outmask_f32, const int* d_box = nullptr) {
+                  const float* outmask_f32, const int* box = nullptr) {
   if (nx < 4 || ny < 4 || nzb < 4)
     return fail(ctx, IFE_E_TOO_SMALL,
                 "recursive Gaussian needs at least 4 samples per axis (got %d x %d x %d)", nx, ny,
                 nzb);
   if (!(sigma > 0.0)) return fail(ctx, IFE_E_INVALID, "sigma must be positive (got %g)", sigma);
   if (keep0 < 0 || keep1 > nzb || keep0 >= keep1) return fail(ctx, IFE_E_INVALID, "bad plane range");
+  // Support box (masked paths, compute_support_box): nothing outside it is ever read, so the z
+  // pass only keeps the box's planes (below them the causal sweep alone runs, above them the
+  // anticausal one), the x pass runs the rows of those planes, and the y pass the columns
+  // (x, z) that cross the box, restricted to its y range.  Columns come in whole warps of 32.
+  int kz0 = keep0, kz1 = keep1, kx0 = 0, kx1 = nx, ky0 = 0, ky1 = ny;
+  if (box) {
+    kz0 = std::max(keep0, box[4]); kz1 = std::min(keep1, box[5]);
+    ky0 = box[2]; ky1 = box[3];
+    if (nx % 32 == 0) { kx0 = box[0] / 32 * 32; kx1 = (box[1] + 31) / 32 * 32; }
+    if (kz0 >= kz1 || ky0 >= ky1 || box[0] >= box[1]) return IFE_OK;   // no voxel is wanted
+  }
   const int nf = cert ? 2 : 1;
   Workspace& ws = ctx->ws;
   const GaussCoef cz = make_gauss_coef(sigma, spacing[2]);
@@ -284,58 +295,48 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   // z pass: lines = nx*ny columns, contiguous across the plane
   A.in0 = in0; A.in1 = cert; A.out0 = a0; A.out1 = a1;
   A.n = nzb; A.stride = (long long)nx * ny; A.na = nx * ny > 0 ? nx * ny : 1; A.sb = 0;
-  A.out_lo = keep0; A.out_hi = keep1;   // a z-slab's halo planes only carry recursion state
+  A.out_lo = kz0; A.out_hi = kz1;   // a z-slab's halo planes only carry recursion state
   A.n_lines = (long long)nx * ny;
-  // support box (masked paths): z pass keeps the box's planes, the x pass runs the rows of those
-  // planes, the y pass the columns (x, z) that cross the box and only its y range
-  A.box = d_box; A.box_a = -1; A.box_b = -1; A.box_o = 2; A.box_b_off = 0;
   if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cz, A)));
   else if (cert_is_u8) IFE_TRY((launch_strided<2, IN_IMG_U8, false>(ctx, cz, A)));
   else IFE_TRY((launch_strided<2, IN_IMG_F32, false>(ctx, cz, A)));
 
-  // x pass: lines = ny*nzk rows, contiguous
-  const int nzk = keep1 - keep0;
-  const size_t koff = (size_t)keep0 * nx * ny;
-  A.in0 = a0 + koff; A.in1 = a1 + koff; A.out0 = b0; A.out1 = b1;
-  A.n = nx; A.stride = 1; A.na = d_box ? ny : 1; A.sb = 0; A.n_lines = (long long)ny * nzk;
+  // x pass: lines = ny*nzk rows, contiguous (b0/b1/out0 hold planes [keep0, keep1): plane kz0
+  // sits at offset kz0 - keep0)
+  const int nzk = kz1 - kz0;
+  const size_t plane = (size_t)nx * ny;
+  const size_t koff = (size_t)kz0 * plane, boff = (size_t)(kz0 - keep0) * plane;
+  A.in0 = a0 + koff; A.in1 = a1 + koff; A.out0 = b0 + boff; A.out1 = b1 + boff;
+  A.n = nx; A.stride = 1; A.na = 1; A.sb = 0; A.n_lines = (long long)ny * nzk;
   A.out_lo = 0; A.out_hi = nx;
-  A.box_a = -1; A.box_b = 2; A.box_o = -1; A.box_b_off = keep0;
   if (nf == 1) IFE_TRY((launch_x<1>(ctx, cx, A)));
   else IFE_TRY((launch_x<2>(ctx, cx, A)));
 
-  // y pass: lines indexed (x, z); base = x + z*nx*ny; stride nx
-  A.in0 = b0; A.in1 = b1; A.out0 = out0; A.out1 = nullptr;
-  A.n = ny; A.stride = nx; A.na = nx; A.sb = (long long)nx * ny; A.n_lines = (long long)nx * nzk;
-  A.out_lo = 0; A.out_hi = ny;
-  A.box_a = 0; A.box_b = 2; A.box_o = 1; A.box_b_off = keep0;
-  A.mask_u8 = outmask_u8; A.mask_f32 = outmask_f32;
+  // y pass: lines indexed (x, z) with x in [kx0, kx1); base = x + z*nx*ny; stride nx
+  const size_t yoff = boff + (size_t)kx0;
+  A.in0 = b0 + yoff; A.in1 = b1 + yoff; A.out0 = out0 + yoff; A.out1 = nullptr;
+  A.n = ny; A.stride = nx; A.na = kx1 - kx0; A.sb = (long long)plane; A.n_lines = (long long)(kx1 - kx0) * nzk;
+  A.out_lo = ky0; A.out_hi = ky1;
+  A.mask_u8 = outmask_u8 ? outmask_u8 + yoff : nullptr;
+  A.mask_f32 = outmask_f32 ? outmask_f32 + yoff : nullptr;
   if (nf == 1) IFE_TRY((launch_strided<1, IN_FIELDS, false>(ctx, cy, A)));
   else IFE_TRY((launch_strided<2, IN_FIELDS, true>(ctx, cy, A)));
   return IFE_OK;
 }
 
-// Support box of `d_mask` (optionally clipped to the bounding box of an ROI list, host array of
-// n_roi x {x,y,z,sx,sy,sz}) for the masked smoothing paths; *d_box stays null when the option
-// is off or the layout does not allow the 16-byte scan (the passes then run everywhere).
+// Support box of `d_mask` (see support_box.cuh), optionally clipped to the bounding box of an
+// ROI list (host array of n_roi x {x,y,z,sx,sy,sz}): box = {x0,x1,y0,y1,z0,z1}, half-open,
+// grown by the stencil reach of one voxel; all zero when no voxel is wanted.  *have stays false
+// when the option is off or the layout does not allow the 16-byte scan (the passes then run
+// everywhere).  Waits for the stream once: the extents come back through pinned memory.
 int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz,
-                        const int* rois, int n_roi, const int** d_box) {
-  *d_box = nullptr;
+                        const int* rois, int n_roi, int box[6], bool* have) {
+  *have = false;
   if (!ctx->use_box || !d_mask || nx % 16 != 0 || reinterpret_cast<uintptr_t>(d_mask) % 16 != 0)
     return IFE_OK;
-  IFE_TRY(ctx->ws.box.reserve(ctx, 12 * sizeof(int)));
+  IFE_TRY(ctx->ws.box.reserve(ctx, 6 * sizeof(int)));
+  if (!ctx->box_host) IFE_CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->box_host, 6 * sizeof(int), cudaHostAllocDefault));
   int* raw = (int*)ctx->ws.box.ptr;
-  int* box = raw + 6;
-  BoxLimits lim;
-  const int n[3] = {nx, ny, nz};
-  for (int d = 0; d < 3; ++d) { lim.lo[d] = 0; lim.hi[d] = n[d]; lim.n[d] = n[d]; }
-  if (n_roi > 0 && rois) {
-    for (int d = 0; d < 3; ++d) { lim.lo[d] = n[d]; lim.hi[d] = 0; }
-    for (int r = 0; r < n_roi; ++r)
-      for (int d = 0; d < 3; ++d) {
-        lim.lo[d] = std::min(lim.lo[d], rois[6 * r + d]);
-        lim.hi[d] = std::max(lim.hi[d], rois[6 * r + d] + rois[6 * r + 3 + d]);
-      }
-  }
   cudaStream_t st = ctx->stream();
   IFE_CUDA_TRY(ctx, cudaMemsetAsync(raw, 0, 6 * sizeof(int), st));
   const long long n_pieces = (long long)nx * ny * nz / 16;
@@ -344,10 +345,34 @@ int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny
     ProfScope prof(ctx, K_OTHER);
     mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_pieces, raw);
   }
-  box_finish_kernel<<<1, 32, 0, st>>>(raw, lim, box);
-  ctx->launches += 2;
+  ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
-  *d_box = box;
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->box_host, raw, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  const int n[3] = {nx, ny, nz};
+  int lo[3], hi[3];
+  bool empty = false;
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = kBoxBig - ctx->box_host[2 * d];
+    hi[d] = ctx->box_host[2 * d + 1];
+  }
+  if (n_roi > 0 && rois) {
+    for (int d = 0; d < 3; ++d) {
+      int rlo = n[d], rhi = 0;
+      for (int r = 0; r < n_roi; ++r) {
+        rlo = std::min(rlo, rois[6 * r + d]);
+        rhi = std::max(rhi, rois[6 * r + d] + rois[6 * r + 3 + d]);
+      }
+      lo[d] = std::max(lo[d], rlo);
+      hi[d] = std::min(hi[d], rhi);
+    }
+  }
+  for (int d = 0; d < 3; ++d) empty = empty || lo[d] >= hi[d];
+  for (int d = 0; d < 3; ++d) {
+    box[2 * d] = empty ? 0 : std::max(lo[d] - 1, 0);
+    box[2 * d + 1] = empty ? 0 : std::min(hi[d] + 1, n[d]);
+  }
+  *have = true;
   return IFE_OK;
 }
 
@@ -393,8 +418,8 @@ constexpr int kManyRois = 192;
 
 // shared memory of the z-march kernel's histogram sink: padded edge rows + private counter columns
 inline size_t march_hist_smem(int nfeat, int n_edges) {
-  return (size_t)nfeat * ((size_t)hist_row_pitch(n_edges) * sizeof(float) +
-                          (size_t)hist_bin_words(n_edges) * 4 * (kMX * kMY));
+  return (size_t)nfeat * ((size_t)hist_edge_pitch(n_edges) * sizeof(float) +
+                          (size_t)((n_edges + 4) / 4) * 4 * (kMX * kMY));
 }
 inline bool march_hist_fits(int nfeat, int n_edges) { return march_hist_smem(nfeat, n_edges) <= 96 * 1024; }
 
@@ -521,6 +546,7 @@ void ife_cuda_destroy(ife_cuda_ctx* ctx) {
   cudaDeviceSynchronize();
   ife_cuda_comm_destroy(ctx);
   ctx->ws.release_all();
+  if (ctx->box_host) cudaFreeHost(ctx->box_host);
   for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->prof_events) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -759,15 +785,16 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
     if (n_sigma > 1) IFE_TRY(ctx->ws.out[1].reserve(ctx, 8 * n * sizeof(float)));
   }
   const StencilCoef S = make_stencil_coef(spacing);
-  const int* d_box;   // all eight outputs are masked: smooth only what in-mask voxels can see
-  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, nullptr, 0, &d_box));
+  int box[6];         // all eight outputs are masked: smooth only what in-mask voxels can see
+  bool have_box;
+  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, nullptr, 0, box, &have_box));
   for (int s = 0; s < n_sigma; ++s) {
     float* blur = (float*)ctx->ws.blur.ptr;
     float* d_out = mem == IFE_MEM_HOST ? (float*)ctx->ws.out[s & 1].ptr : out + (size_t)s * 8 * n;
     if (mem == IFE_MEM_HOST && s >= 2)  // the staging buffer must have been drained
       IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream(), ctx->events[2 + (s & 1)], 0));
     IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                          nullptr, nullptr, d_box));
+                          nullptr, nullptr, have_box ? box : nullptr));
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
     A.vol = blur; A.mask_u8 = d_mask;
@@ -842,12 +869,13 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
                          (long long)nx * ny < (1LL << 28);
   if (many_rois) IFE_TRY(ctx->ws.packed.reserve(ctx, n * sizeof(unsigned long long)));
   const StencilCoef S = make_stencil_coef(spacing);
-  const int* d_box;   // only in-mask voxels (inside some ROI, when there are ROIs) are binned
-  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, rois, n_roi, &d_box));
+  int box[6];         // only in-mask voxels (inside some ROI, when there are ROIs) are binned
+  bool have_box;
+  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, rois, n_roi, box, &have_box));
   for (int s = 0; s < n_sigma; ++s) {
     float* blur = (float*)ctx->ws.blur.ptr;
     IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                          nullptr, nullptr, d_box));
+                          nullptr, nullptr, have_box ? box : nullptr));
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
     A.vol = blur; A.mask_u8 = d_mask;
@@ -940,13 +968,14 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
     const uint8_t* d_mask = (const uint8_t*)mask_slot[k]->ptr;
     uint32_t* d_counts = (uint32_t*)ws.counts.ptr + (size_t)k * n_counts;
     IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), st));
-    const int* d_box;
+    int box[6];
+    bool have_box;
     IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr,
-                                n_roi, &d_box));
+                                n_roi, box, &have_box));
     for (int s = 0; s < n_sigma; ++s) {
       float* blur = (float*)ws.blur.ptr;
       IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                            nullptr, nullptr, d_box));
+                            nullptr, nullptr, have_box ? box : nullptr));
       FeatArgs A;
       std::memset(&A, 0, sizeof(A));
       A.vol = blur; A.mask_u8 = d_mask;

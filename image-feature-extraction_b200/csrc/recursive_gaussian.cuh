@@ -322,35 +322,7 @@ struct PassArgs {
   int na;               // lines are indexed l = a + na*b, base = a + b*sb  (strided pass)
   long long sb;
   long long n_lines;
-  // Optional support box of the output mask (device memory, written by support_box.cuh):
-  // {x0,x1,y0,y1,z0,z1}, half-open, already dilated by the stencil reach.  Results outside it
-  // are never read (every consumer masks them), so the software-pipelined kernels skip whole
-  // warps of lines that miss it and shrink the output range along the line to it.  box_a /
-  // box_b / box_o name the box axis (0,1,2; -1 = unbounded) that bounds a = line % na,
-  // b = line / na + box_b_off and the position along the line.  Kernels may ignore the box.
-  const int* box;
-  int box_a, box_b, box_o, box_b_off;
 };
-
-// warp-uniform: does any of the 32 lines starting at line `wl` (same b) touch the box, and
-// which part [out_lo, out_hi) of the line is wanted
-__device__ __forceinline__ bool box_wants_warp(const PassArgs& A, long long wl, int& out_lo, int& out_hi) {
-  if (!A.box) return true;
-  if (A.box_o >= 0) {
-    out_lo = max(out_lo, A.box[2 * A.box_o]);
-    out_hi = min(out_hi, A.box[2 * A.box_o + 1]);
-  }
-  bool need = out_lo < out_hi;
-  if (A.box_a >= 0) {
-    const long long a = wl % A.na;
-    need = need && a + 32 > A.box[2 * A.box_a] && a < A.box[2 * A.box_a + 1];
-  }
-  if (A.box_b >= 0) {
-    const long long b = wl / A.na + A.box_b_off;
-    need = need && b >= A.box[2 * A.box_b] && b < A.box[2 * A.box_b + 1];
-  }
-  return need;
-}
 
 template <int NF, int INMODE>
 __device__ __forceinline__ void load_sample(const PassArgs& A, size_t idx, float (&v)[NF]) {
@@ -659,10 +631,8 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
 
   // chunks [0, kA) need the causal sweep (nothing above the output range does); chunks
   // [k_lo, n_chunks) the anticausal one; only chunks in [k_lo, kA) produce output
-  int out_lo = A.out_lo, out_hi = A.out_hi;
-  if (!box_wants_warp(A, wl, out_lo, out_hi)) return;   // the whole warp leaves (no block barriers here)
-  const int kA = min(n_chunks, (out_hi + L - 1) / L);
-  const int k_lo = max(0, out_lo) / L;
+  const int kA = min(n_chunks, (A.out_hi + L - 1) / L);
+  const int k_lo = max(0, A.out_lo) / L;
 
   // copies of chunk kc into a stage: predicate-free for interior chunks of full warps
   const bool warp_full = wline + 32 <= A.n_lines;
@@ -1048,11 +1018,6 @@ gauss_pass_x_async(const __grid_constant__ GaussCoef C, const __grid_constant__ 
   XOut<NF, L>& O = reinterpret_cast<XOut<NF, L>*>(reinterpret_cast<XStage<NF, L>*>(xasync_smem) + WARPS * STAGES)[warp];
   const long long line0 = ((long long)blockIdx.x * WARPS + warp) * 32;
   if (line0 >= A.n_lines) return;   // whole warp exits together
-  if (A.box && A.box_b >= 0) {      // x lines of planes outside the support box are never read
-    const long long last = min(line0 + 31, A.n_lines - 1);
-    const long long b0 = line0 / A.na + A.box_b_off, b1 = last / A.na + A.box_b_off;
-    if (b1 < A.box[2 * A.box_b] || b0 >= A.box[2 * A.box_b + 1]) return;
-  }
   const long long line = line0 + lane;
   const bool active = line < A.n_lines;
   const int n = A.n;

@@ -8,8 +8,9 @@
 // inside the mask's bounding box grown by one voxel.  The recursion itself has infinite
 // support and must still run along complete lines, but lines that miss the box need not run at
 // all and, along a line, nothing below the box needs the anticausal sweep and nothing above it
-// the causal one (recursive_gaussian.cuh: PassArgs::box).  The box is found on the device and
-// read by the passes from device memory, so no call waits for the host.
+// the causal one.  The extents are reduced on the device (this kernel) and read back once per
+// call; the host turns them into pointer offsets, line counts and output ranges of the
+// unchanged pass kernels (smooth_volume in ife_cuda.cu).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -56,29 +57,6 @@ mask_box_kernel(const uint8_t* __restrict__ mask, int nx, int ny, long long n_pi
     atomicMax(raw + 0, kBoxBig - xlo); atomicMax(raw + 1, xhi);
     atomicMax(raw + 2, kBoxBig - ylo); atomicMax(raw + 3, yhi);
     atomicMax(raw + 4, kBoxBig - zlo); atomicMax(raw + 5, zhi);
-  }
-}
-
-struct BoxLimits {
-  int lo[3], hi[3];   // only voxels inside [lo, hi) count (the bounding box of an ROI list)
-  int n[3];
-};
-
-// raw extents -> box[6] = {x0,x1,y0,y1,z0,z1}: clipped to the limits, grown by the stencil
-// reach of one voxel, clipped to the volume; all zero when nothing is wanted
-__global__ void box_finish_kernel(const int* __restrict__ raw, const __grid_constant__ BoxLimits lim,
-                                  int* __restrict__ box) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int lo[3], hi[3];
-  bool empty = false;
-  for (int d = 0; d < 3; ++d) {
-    lo[d] = max(kBoxBig - raw[2 * d], lim.lo[d]);
-    hi[d] = min(raw[2 * d + 1], lim.hi[d]);
-    empty = empty || lo[d] >= hi[d];
-  }
-  for (int d = 0; d < 3; ++d) {
-    box[2 * d] = empty ? 0 : max(lo[d] - 1, 0);
-    box[2 * d + 1] = empty ? 0 : min(hi[d] + 1, lim.n[d]);
   }
 }
 

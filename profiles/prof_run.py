@@ -1,5 +1,5 @@
 """Short single-GPU run for ncu: the flagship path at full size (512x512x400), one scale per
-call, device-resident inputs.  Usage: python profiles/prof_run.py [sigma ...] [--hist]"""
+call, device-resident inputs.  Usage: python profiles/prof_run.py [sigma ...] [--hist [--eq]] [--lung] [--plain]"""
 import os
 import sys
 
@@ -23,7 +23,11 @@ for it in range(2):
     ctx.emphysema_features_dev(img.data_ptr(), mask.data_ptr(), out.data_ptr(), bench.DIMS, sigmas)
     ctx.synchronize()
 if "--hist" in sys.argv:
-    edges = np.tile(np.linspace(-1.0, 1.0, 40, dtype=np.float32), (len(sigmas) * 8, 1))
+    if "--eq" in sys.argv:    # equal-frequency edges of this scan, as MakeBag gets them
+        i0 = bench.SIGMAS.index(sigmas[0]) * 8
+        edges = bench.equalized_edges_from_scan(torch, ctx, img, mask, 40)[i0:i0 + 8 * len(sigmas)].copy()
+    else:
+        edges = np.tile(np.linspace(-1.0, 1.0, 40, dtype=np.float32), (len(sigmas) * 8, 1))
     counts = torch.zeros((1, len(sigmas) * 8, 41), dtype=torch.int32, device=dev)
     ctx.emphysema_histograms_dev(img.data_ptr(), mask.data_ptr(), counts.data_ptr(), bench.DIMS, sigmas, edges)
     ctx.synchronize()
