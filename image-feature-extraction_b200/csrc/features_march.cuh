@@ -59,10 +59,11 @@ __device__ __forceinline__ unsigned opaque_u32(unsigned v) {
   return v;
 }
 
-// MODE / HIST / UNIT / ALLOUT as in features_kernel.  HIST here is the whole-volume
+// MODE / HIST / UNIT as in features_kernel.  HIST here is the whole-volume
 // histogram only (A.hist.n_roi == 0); ROI lists stay with the brick kernel, whose culling of
 // bricks that touch no ROI is worth more than the march.  Masks: uint8 or none.
-template <int MODE, bool HIST, bool UNIT, bool ALLOUT>
+// OUTS: 1 = every output plane pointer is set, 2 = none is (histograms only), 0 = test each
+template <int MODE, bool HIST, bool UNIT, int OUTS>
 __global__ void __launch_bounds__(kMX * kMY, HIST ? IFE_MARCH_MINB_HIST : IFE_MARCH_MINB)
 features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_constant__ FeatArgs A,
                       const int zchunk) {
@@ -72,23 +73,26 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
   __shared__ __align__(16) unsigned char s_mask[4][kMX * kMY];   // the mask bytes of the same planes
   extern __shared__ unsigned char feat_smem[];
   // Histogram sink.  Shared-memory atomics run at about one lane per clock per SM, far too
-  // slow for eight inserts per voxel, so there are none: every thread owns a private column of
-  // 8-bit counters, four to a word, word q of thread t at s_priv[q*NT + t] (a warp's 32 lanes
-  // always hit 32 different banks), an insert is a plain load/add/store, and a thread sees at
-  // most zchunk <= 255 voxels, so a counter cannot overflow.  Columns are summed once per block.
+  // slow for eight inserts per voxel, so there are none: every thread owns a private 8-bit
+  // counter per (feature, bin), byte (tid >> 5) of word [(k*nb + bin)*32 + (tid & 31)] -- a
+  // warp's 32 lanes always hit 32 different banks whatever their bins, the four warps of the
+  // block own the four bytes of a word -- an insert is a byte load/add/store at
+  // (bin << 7) + a per-thread constant, and a thread sees at most zchunk <= 255 voxels, so a
+  // counter cannot overflow.  Rows are summed once per block.
   float* s_edges = reinterpret_cast<float*>(feat_smem);          // rows padded with +inf to ep = 2^k
   const int ep = hist_edge_pitch(A.hist.n_edges);
   unsigned* s_priv = reinterpret_cast<unsigned*>(s_edges + NFEAT * ep);
   const int nb = A.hist.n_edges + 1;
-  const int nbq = (nb + 3) / 4;                  // words per feature in a private column
-  const int nq = NFEAT * nbq;                    // (features never share a word)
   const int tid = threadIdx.y * kMX + threadIdx.x;
+  // this thread's counter of (feature 0, bin 0), as a byte offset from s_edges (everything the
+  // sink touches is addressed by 32-bit offsets from that one shared-memory base)
+  const unsigned cnt0 = (unsigned)(NFEAT * ep) * 4u + (unsigned)((tid & 31) * 4 + (tid >> 5));
   if (HIST) {
     for (int i = tid; i < NFEAT * ep; i += NT) {
       const int k = i / ep, j = i - k * ep;
       s_edges[i] = j < A.hist.n_edges ? A.hist.edges[k * A.hist.n_edges + j] : __int_as_float(0x7f800000);
     }
-    for (int i = tid; i < nq * NT; i += NT) s_priv[i] = 0u;
+    for (int i = tid; i < NFEAT * nb * 32; i += NT) s_priv[i] = 0u;
   }
 
   const int nx = A.nx, ny = A.ny;
@@ -254,7 +258,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
 #else
 #pragma unroll
         for (int k = 0; k < NFEAT; ++k)
-          if (ALLOUT || A.out[k]) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = f[k];
+          if (OUTS == 1 || (OUTS == 0 && A.out[k])) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = f[k];
 #endif
       } else {
 #pragma unroll
@@ -262,46 +266,46 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
         if (in_xy) {
 #pragma unroll
           for (int k = 0; k < NFEAT; ++k)
-            if (ALLOUT || A.out[k]) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = 0.0f;
+            if (OUTS == 1 || (OUTS == 0 && A.out[k])) *reinterpret_cast<float*>(reinterpret_cast<char*>(po) + dk[k] * 4) = 0.0f;
         }
       }
       if (HIST && C.inside) {
-        // eight independent searches, then eight loads, then eight stores: the words are
-        // distinct by construction, so nothing here waits on anything but its own feature
-        int bin[NFEAT];
+        // eight independent searches, then eight counter updates: nothing here waits on
+        // anything but its own feature.  off[k] = 4 * (number of edges < f[k]).
+        unsigned off[NFEAT];
+        const char* eb = reinterpret_cast<const char*>(s_edges);
         if (ep == 64) {
           // step-major order: the eight searches advance together, so the eight loads of a
-          // step are in flight at once instead of 48 dependent loads back to back
-          const float* p[NFEAT];
+          // step are in flight at once instead of 48 dependent loads back to back; a step is
+          // a load at an immediate offset, a compare and a predicated add
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) p[k] = s_edges + k * 64;
+          for (int k = 0; k < NFEAT; ++k) off[k] = 0u;
 #pragma unroll
           for (int step = 32; step >= 1; step >>= 1) {
             float ev[NFEAT];
 #pragma unroll
-            for (int k = 0; k < NFEAT; ++k) ev[k] = p[k][step - 1];
+            for (int k = 0; k < NFEAT; ++k)
+              ev[k] = *reinterpret_cast<const float*>(eb + off[k] + (unsigned)(k * 256 + (step - 1) * 4));
 #pragma unroll
             for (int k = 0; k < NFEAT; ++k)
-              if (ev[k] < f[k]) p[k] += step;
+              if (ev[k] < f[k]) off[k] += (unsigned)(step * 4);
           }
-#pragma unroll
-          for (int k = 0; k < NFEAT; ++k) bin[k] = (int)(p[k] - (s_edges + k * 64));
         } else {
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) bin[k] = dense_bin_padded_rt(s_edges + k * ep, ep, f[k]);
+          for (int k = 0; k < NFEAT; ++k) off[k] = 4u * (unsigned)dense_bin_padded_rt(s_edges + k * ep, ep, f[k]);
         }
         if (A.hist.packed) {
           unsigned long long w = 0;
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) w |= (unsigned long long)(unsigned)bin[k] << (8 * k);
+          for (int k = 0; k < NFEAT; ++k) w |= (unsigned long long)(off[k] >> 2) << (8 * k);
           A.hist.packed[pkz + vox_pk] = w;
         } else {
-          unsigned wv[NFEAT];
+          unsigned char* cb = reinterpret_cast<unsigned char*>(s_edges) + cnt0;
+          unsigned cv[NFEAT];
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k) wv[k] = s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid];
+          for (int k = 0; k < NFEAT; ++k) cv[k] = cb[(unsigned)(k * nb) * 128u + (off[k] << 5)];
 #pragma unroll
-          for (int k = 0; k < NFEAT; ++k)
-            s_priv[(k * nbq + (bin[k] >> 2)) * NT + tid] = wv[k] + (1u << ((bin[k] & 3) * 8));
+          for (int k = 0; k < NFEAT; ++k) cb[(unsigned)(k * nb) * 128u + (off[k] << 5)] = (unsigned char)(cv[k] + 1u);
         }
       } else if (HIST && A.hist.packed && in_xy) {
         A.hist.packed[pkz + vox_pk] = ~0ull;              // outside the mask
@@ -324,14 +328,12 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
 
   if (HIST) {
     __syncthreads();
-    // thread i sums counter row i over the NT columns
+    // thread i sums counter row i = (feature, bin): 32 words of four 8-bit counters each
     for (int i = tid; i < NFEAT * nb; i += NT) {
-      const int k = i / nb, bn = i - k * nb;
-      const unsigned* w = s_priv + (k * nbq + (bn >> 2)) * NT;
-      const unsigned sh = (bn & 3) * 8;
+      const unsigned* w = s_priv + i * 32;
       unsigned total = 0;
 #pragma unroll 8
-      for (int j = 0; j < NT; ++j) total += (w[(j + tid) & (NT - 1)] >> sh) & 0xffu;
+      for (int j = 0; j < 32; ++j) total = __dp4a(w[(j + tid) & 31], 0x01010101u, total);
       if (total) atomicAdd(A.hist.counts + i, total);
     }
   }

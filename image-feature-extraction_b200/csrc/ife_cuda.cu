@@ -396,16 +396,17 @@ template <int MODE, bool HIST>
 void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                        const StencilCoef& S, const FeatArgs& A, int zchunk) {
   constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
-  bool all = true;
-  for (int k = 0; k < NFEAT; ++k) all = all && A.out[k] != nullptr;
+  bool all = true, none = true;
+  for (int k = 0; k < NFEAT; ++k) { all = all && A.out[k] != nullptr; none = none && A.out[k] == nullptr; }
   if (zchunk > 0) {   // z-marching kernel (everything but ROI-list histograms)
     auto go = [&](void (*kern)(StencilCoef, FeatArgs, int)) {
       if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       kern<<<grid, block, smem, st>>>(S, A, zchunk);
     };
-    if (all && unit) go(features_march_kernel<MODE, HIST, true, true>);
-    else if (unit) go(features_march_kernel<MODE, HIST, true, false>);
-    else go(features_march_kernel<MODE, HIST, false, false>);
+    if (HIST && none && unit) go(features_march_kernel<MODE, HIST, true, HIST ? 2 : 0>);   // histograms only
+    else if (all && unit) go(features_march_kernel<MODE, HIST, true, 1>);
+    else if (unit) go(features_march_kernel<MODE, HIST, true, 0>);
+    else go(features_march_kernel<MODE, HIST, false, 0>);
     return;
   }
   if (all && unit) features_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A);
@@ -419,7 +420,7 @@ constexpr int kManyRois = 192;
 // shared memory of the z-march kernel's histogram sink: padded edge rows + private counter columns
 inline size_t march_hist_smem(int nfeat, int n_edges) {
   return (size_t)nfeat * ((size_t)hist_edge_pitch(n_edges) * sizeof(float) +
-                          (size_t)((n_edges + 4) / 4) * 4 * (kMX * kMY));
+                          (size_t)(n_edges + 1) * (kMX * kMY));   // one byte per (bin, thread)
 }
 inline bool march_hist_fits(int nfeat, int n_edges) { return march_hist_smem(nfeat, n_edges) <= 96 * 1024; }
 
