@@ -332,18 +332,19 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
 int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz,
                         const int* rois, int n_roi, int box[6], bool* have) {
   *have = false;
-  if (!ctx->use_box || !d_mask || nx % 16 != 0 || reinterpret_cast<uintptr_t>(d_mask) % 16 != 0)
+  if (!ctx->use_box || !d_mask || nx % 16 != 0 || reinterpret_cast<uintptr_t>(d_mask) % 16 != 0 ||
+      (long long)ny * nz >= (1LL << 31))
     return IFE_OK;
   IFE_TRY(ctx->ws.box.reserve(ctx, 6 * sizeof(int)));
   if (!ctx->box_host) IFE_CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->box_host, 6 * sizeof(int), cudaHostAllocDefault));
   int* raw = (int*)ctx->ws.box.ptr;
   cudaStream_t st = ctx->stream();
   IFE_CUDA_TRY(ctx, cudaMemsetAsync(raw, 0, 6 * sizeof(int), st));
-  const long long n_pieces = (long long)nx * ny * nz / 16;
-  const unsigned grid = (unsigned)std::min<long long>((n_pieces + 255) / 256, 8LL * ctx->sm_count);
+  const unsigned n_rows = (unsigned)((long long)ny * nz);
+  const unsigned grid = (unsigned)std::min<long long>(((long long)n_rows + 7) / 8, 8LL * ctx->sm_count);
   {
     ProfScope prof(ctx, K_OTHER);
-    mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_pieces, raw);
+    mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_rows, raw);
   }
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());

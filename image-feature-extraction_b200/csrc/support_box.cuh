@@ -21,33 +21,36 @@ constexpr int kBoxBig = 1 << 30;
 
 // raw[2*d] = max(kBoxBig - min coordinate), raw[2*d+1] = max(coordinate + 1) over the non-zero
 // voxels; all zero (as cudaMemsetAsync leaves it) = no voxel yet.
-// Requires nx % 16 == 0 and a 16-byte aligned mask: a thread tests 16 voxels of one row.
+// Requires nx % 16 == 0 and a 16-byte aligned mask.  A warp walks rows (y, z); a lane tests 16
+// voxels of the row with one 16-byte load.
 __global__ void __launch_bounds__(256)
-mask_box_kernel(const uint8_t* __restrict__ mask, int nx, int ny, long long n_pieces, int* __restrict__ raw) {
+mask_box_kernel(const uint8_t* __restrict__ mask, int nx, int ny, unsigned n_rows, int* __restrict__ raw) {
   const int ppr = nx >> 4;   // 16-byte pieces per row
   int xlo = kBoxBig, xhi = 0, ylo = kBoxBig, yhi = 0, zlo = kBoxBig, zhi = 0;
   const uint4* m16 = reinterpret_cast<const uint4*>(mask);
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pieces;
-       p += (long long)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(m16 + p);
-    if ((v.x | v.y | v.z | v.w) == 0u) continue;
-    const unsigned w[4] = {v.x, v.y, v.z, v.w};
-    int first = 16, last = -1;
+  const int lane = threadIdx.x & 31;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
+    const int z = (int)(row / (unsigned)ny), y = (int)(row - (unsigned)z * (unsigned)ny);
+    const uint4* mr = m16 + (size_t)row * (size_t)ppr;
+    for (int pc = lane; pc < ppr; pc += 32) {
+      const uint4 v = __ldg(mr + pc);
+      if ((v.x | v.y | v.z | v.w) == 0u) continue;
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
+      int first = 16, last = -1;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // bit 7 of every non-zero byte
-      const unsigned t = (w[k] | ((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
-      if (t) {
-        first = min(first, 4 * k + ((__ffs(t) - 1) >> 3));
-        last = max(last, 4 * k + ((31 - __clz(t)) >> 3));
+      for (int k = 0; k < 4; ++k) {
+        // bit 7 of every non-zero byte
+        const unsigned t = (w[k] | ((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+        if (t) {
+          first = min(first, 4 * k + ((__ffs(t) - 1) >> 3));
+          last = max(last, 4 * k + ((31 - __clz(t)) >> 3));
+        }
       }
+      xlo = min(xlo, 16 * pc + first); xhi = max(xhi, 16 * pc + last + 1);
+      ylo = min(ylo, y); yhi = max(yhi, y + 1);
+      zlo = min(zlo, z); zhi = max(zhi, z + 1);
     }
-    const long long row = p / ppr;
-    const int x0 = (int)(p - row * ppr) << 4;
-    const int y = (int)(row % ny), z = (int)(row / ny);
-    xlo = min(xlo, x0 + first); xhi = max(xhi, x0 + last + 1);
-    ylo = min(ylo, y); yhi = max(yhi, y + 1);
-    zlo = min(zlo, z); zhi = max(zhi, z + 1);
   }
   const unsigned full = 0xffffffffu;
   xlo = __reduce_min_sync(full, xlo); xhi = __reduce_max_sync(full, xhi);
