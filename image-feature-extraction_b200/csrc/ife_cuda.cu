@@ -324,38 +324,46 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   return IFE_OK;
 }
 
-// Support box of `d_mask` (see support_box.cuh), optionally clipped to the bounding box of an
-// ROI list (host array of n_roi x {x,y,z,sx,sy,sz}): box = {x0,x1,y0,y1,z0,z1}, half-open,
-// grown by the stencil reach of one voxel; all zero when no voxel is wanted.  *have stays false
-// when the option is off or the layout does not allow the 16-byte scan (the passes then run
-// everywhere).  Waits for the stream once: the extents come back through pinned memory.
-int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz,
-                        const int* rois, int n_roi, int box[6], bool* have) {
-  *have = false;
-  if (!ctx->use_box || !d_mask || nx % 16 != 0 || reinterpret_cast<uintptr_t>(d_mask) % 16 != 0 ||
-      (long long)ny * nz >= (1LL << 31))
-    return IFE_OK;
-  IFE_TRY(ctx->ws.box.reserve(ctx, 6 * sizeof(int)));
-  if (!ctx->box_host) IFE_CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->box_host, 6 * sizeof(int), cudaHostAllocDefault));
-  int* raw = (int*)ctx->ws.box.ptr;
-  cudaStream_t st = ctx->stream();
+// Support box of a mask (see support_box.cuh).  Three steps so that a batch can run the
+// reduction on its copy stream right behind the upload of the mask:
+//   support_box_usable  option on and the layout allows the 16-byte scan (else the passes run
+//                       everywhere);
+//   launch_support_box  reduction kernel + read-back of the six extents into pinned slot
+//                       `slot` (0 or 1), on stream `st`;
+//   finish_support_box  after `st` got there: box = {x0,x1,y0,y1,z0,z1}, half-open, clipped to
+//                       the bounding box of an ROI list (host array of n_roi x {x,y,z,sx,sy,sz})
+//                       when there is one, grown by the stencil reach of one voxel; all zero
+//                       when no voxel is wanted.
+bool support_box_usable(const ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz) {
+  return ctx->use_box && d_mask && nx % 16 == 0 && reinterpret_cast<uintptr_t>(d_mask) % 16 == 0 &&
+         (long long)ny * nz < (1LL << 31);
+}
+
+int launch_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz,
+                       cudaStream_t st, int slot) {
+  IFE_TRY(ctx->ws.box.reserve(ctx, 12 * sizeof(int)));
+  if (!ctx->box_host)
+    IFE_CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->box_host, 12 * sizeof(int), cudaHostAllocDefault));
+  int* raw = (int*)ctx->ws.box.ptr + 6 * slot;
   IFE_CUDA_TRY(ctx, cudaMemsetAsync(raw, 0, 6 * sizeof(int), st));
   const unsigned n_rows = (unsigned)((long long)ny * nz);
   const unsigned grid = (unsigned)std::min<long long>(((long long)n_rows + 7) / 8, 8LL * ctx->sm_count);
-  {
-    ProfScope prof(ctx, K_OTHER);
-    mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_rows, raw);
-  }
+  mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_rows, raw);
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
-  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->box_host, raw, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->box_host + 6 * slot, raw, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return IFE_OK;
+}
+
+void finish_support_box(const ife_cuda_ctx* ctx, int slot, int nx, int ny, int nz, const int* rois,
+                        int n_roi, int box[6]) {
+  const int* h = ctx->box_host + 6 * slot;
   const int n[3] = {nx, ny, nz};
   int lo[3], hi[3];
   bool empty = false;
   for (int d = 0; d < 3; ++d) {
-    lo[d] = kBoxBig - ctx->box_host[2 * d];
-    hi[d] = ctx->box_host[2 * d + 1];
+    lo[d] = kBoxBig - h[2 * d];
+    hi[d] = h[2 * d + 1];
   }
   if (n_roi > 0 && rois) {
     for (int d = 0; d < 3; ++d) {
@@ -373,7 +381,16 @@ int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny
     box[2 * d] = empty ? 0 : std::max(lo[d] - 1, 0);
     box[2 * d + 1] = empty ? 0 : std::min(hi[d] + 1, n[d]);
   }
-  *have = true;
+}
+
+// the three steps on the context's stream; waits for the stream once
+int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny, int nz,
+                        const int* rois, int n_roi, int box[6], bool* have) {
+  *have = support_box_usable(ctx, d_mask, nx, ny, nz);
+  if (!*have) return IFE_OK;
+  IFE_TRY(launch_support_box(ctx, d_mask, nx, ny, nz, ctx->stream(), 0));
+  IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  finish_support_box(ctx, 0, nx, ny, nz, rois, n_roi, box);
   return IFE_OK;
 }
 
@@ -951,12 +968,17 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
   if (n_roi > 0)
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ws.rois.ptr, rois, (size_t)n_scans * n_roi * 6 * sizeof(int),
                                       cudaMemcpyHostToDevice, st));
+  const bool use_box = support_box_usable(ctx, (const uint8_t*)mask_slot[0]->ptr, nx, ny, nz) &&
+                       support_box_usable(ctx, (const uint8_t*)mask_slot[1]->ptr, nx, ny, nz);
   // events[0..1]: upload of slot k done; events[2..3]: kernels reading slot k done
   auto upload = [&](int i) -> int {
     const int k = i & 1;
     if (i >= 2) IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(cp, ctx->events[2 + k], 0));
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(img_slot[k]->ptr, images[i], n * sizeof(float), cudaMemcpyHostToDevice, cp));
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_slot[k]->ptr, masks[i], n, cudaMemcpyHostToDevice, cp));
+    // the mask's support box is reduced right behind its upload, so the host never has to
+    // wait for the kernels of the scan before
+    if (use_box) IFE_TRY(launch_support_box(ctx, (const uint8_t*)mask_slot[k]->ptr, nx, ny, nz, cp, k));
     IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[k], cp));
     return IFE_OK;
   };
@@ -971,9 +993,11 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
     uint32_t* d_counts = (uint32_t*)ws.counts.ptr + (size_t)k * n_counts;
     IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), st));
     int box[6];
-    bool have_box;
-    IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr,
-                                n_roi, box, &have_box));
+    const bool have_box = use_box;
+    if (use_box) {
+      IFE_CUDA_TRY(ctx, cudaEventSynchronize(ctx->events[k]));   // upload i and its box are in
+      finish_support_box(ctx, k, nx, ny, nz, n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr, n_roi, box);
+    }
     for (int s = 0; s < n_sigma; ++s) {
       float* blur = (float*)ws.blur.ptr;
       IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],

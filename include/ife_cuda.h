@@ -90,7 +90,13 @@ uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx);
 
 /* Tuning / debugging switches.  "async_passes" (default 1): use the cp.async software-
  * pipelined Gaussian pass kernels; 0 selects the plain register-staged kernels (same
- * results bit for bit; kept as the fallback for layouts the pipelined kernels reject). */
+ * results bit for bit; kept as the fallback for layouts the pipelined kernels reject).
+ * "support_box" (default 1): the calls whose every result is masked
+ * (ife_cuda_emphysema_features / _histograms / _histograms_batch) smooth only what an in-mask
+ * voxel can see -- the mask's bounding box (clipped to the ROI list's, when there is one)
+ * grown by the one-voxel stencil reach; the box is reduced on the device and read back once
+ * per call, which makes these calls wait for the stream once.  0 smooths the whole volume
+ * (same results bit for bit). */
 int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value);
 
 /* Optional per-kernel timing for benchmarks: while enabled, every kernel launch of the
