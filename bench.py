@@ -527,7 +527,7 @@ def _main(out_stream):
         if hist:
             # BASELINE.json configs[4] on this GPU: a batch of host-resident scans through
             # ife_cuda_emphysema_histograms_batch (upload of scan i+1 behind the kernels of scan i)
-            nb = 4
+            nb = 8                               # configs[4]: 64 scans over 8 GPUs = 8 scans per GPU
             imgs = [h_img.numpy()] * nb          # the same pinned scan nb times: identical traffic
             masks = [h_mask.numpy()] * nb
             rois_b = None if rois is None else np.stack([rois] * nb)
