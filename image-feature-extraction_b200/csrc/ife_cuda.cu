@@ -347,7 +347,7 @@ int launch_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny,
   int* raw = (int*)ctx->ws.box.ptr + 6 * slot;
   IFE_CUDA_TRY(ctx, cudaMemsetAsync(raw, 0, 6 * sizeof(int), st));
   const unsigned n_rows = (unsigned)((long long)ny * nz);
-  const unsigned grid = (unsigned)std::min<long long>(((long long)n_rows + 7) / 8, 8LL * ctx->sm_count);
+  const unsigned grid = (unsigned)std::min<long long>(((long long)n_rows + 31) / 32, 8LL * ctx->sm_count);
   mask_box_kernel<<<grid, 256, 0, st>>>(d_mask, nx, ny, n_rows, raw);
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());

@@ -30,26 +30,33 @@ mask_box_kernel(const uint8_t* __restrict__ mask, int nx, int ny, unsigned n_row
   const uint4* m16 = reinterpret_cast<const uint4*>(mask);
   const int lane = threadIdx.x & 31;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
-    const int z = (int)(row / (unsigned)ny), y = (int)(row - (unsigned)z * (unsigned)ny);
-    const uint4* mr = m16 + (size_t)row * (size_t)ppr;
+  // four rows per trip: the four 16-byte loads of a lane are in flight together
+  for (unsigned row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4u; row0 < n_rows; row0 += n_warps * 4u) {
     for (int pc = lane; pc < ppr; pc += 32) {
-      const uint4 v = __ldg(mr + pc);
-      if ((v.x | v.y | v.z | v.w) == 0u) continue;
-      const unsigned w[4] = {v.x, v.y, v.z, v.w};
-      int first = 16, last = -1;
+      uint4 v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // bit 7 of every non-zero byte
-        const unsigned t = (w[k] | ((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
-        if (t) {
-          first = min(first, 4 * k + ((__ffs(t) - 1) >> 3));
-          last = max(last, 4 * k + ((31 - __clz(t)) >> 3));
+      for (int u = 0; u < 4; ++u)
+        v[u] = row0 + u < n_rows ? __ldg(m16 + (size_t)(row0 + u) * (size_t)ppr + pc) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0u) continue;
+        const unsigned w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        int first = 16, last = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // bit 7 of every non-zero byte
+          const unsigned t = (w[k] | ((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+          if (t) {
+            first = min(first, 4 * k + ((__ffs(t) - 1) >> 3));
+            last = max(last, 4 * k + ((31 - __clz(t)) >> 3));
+          }
         }
+        const unsigned row = row0 + u;
+        const int z = (int)(row / (unsigned)ny), y = (int)(row - (unsigned)z * (unsigned)ny);
+        xlo = min(xlo, 16 * pc + first); xhi = max(xhi, 16 * pc + last + 1);
+        ylo = min(ylo, y); yhi = max(yhi, y + 1);
+        zlo = min(zlo, z); zhi = max(zhi, z + 1);
       }
-      xlo = min(xlo, 16 * pc + first); xhi = max(xhi, 16 * pc + last + 1);
-      ylo = min(ylo, y); yhi = max(yhi, y + 1);
-      zlo = min(zlo, z); zhi = max(zhi, z + 1);
     }
   }
   const unsigned full = 0xffffffffu;
