@@ -365,6 +365,7 @@ def _main(out_stream):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-box", action="store_true", help="A/B: smooth the whole volume even where the mask cannot see it")
+    ap.add_argument("--overlap", action="store_true", help="option overlap_scales: features of scale s beside the passes of scale s+1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out_stream)
@@ -392,6 +393,8 @@ def _main(out_stream):
     ctx.set_stream(stream.cuda_stream)
     if args.no_box:
         ctx.set_option("support_box", 0)
+    if args.overlap:
+        ctx.set_option("overlap_scales", 1)
     if args.workload == "slab":
         return run_slab(args, torch, dist, ctx, stream, dev, world, rank, local_rank, warmup, out_stream)
     nx, ny, nz = DIMS

@@ -21,7 +21,7 @@ struct DeviceBuffer {
 
 struct Workspace {
   DeviceBuffer a0, a1, b0, b1;  // float volumes between the z, x and y passes (two fields)
-  DeviceBuffer blur;            // smoothed volume fed to the fused feature kernel
+  DeviceBuffer blur, blur2;     // smoothed volume fed to the fused feature kernel (blur2: option overlap_scales)
   DeviceBuffer ckpt;            // recursion checkpoints (double)
   DeviceBuffer in_img, in_mask; // staging for IFE_MEM_HOST inputs
   DeviceBuffer out[2];          // staging for IFE_MEM_HOST outputs (double-buffered per scale)
@@ -31,7 +31,7 @@ struct Workspace {
   DeviceBuffer box;             // raw extents[6] of the output mask (support_box.cuh)
   void release_all() {
     DeviceBuffer* all[] = {&a0, &a1, &b0, &b1, &blur, &ckpt, &in_img, &in_mask, &out[0], &out[1],
-                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box};
+                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box, &blur2};
     for (DeviceBuffer* b : all) b->release();
   }
 };
@@ -57,13 +57,17 @@ struct ife_cuda_ctx {
   int arith = 1;  // IFE_ARITH_FMA
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t hp_stream = nullptr;    // highest priority: the Gaussian passes of option "overlap_scales"
+  cudaStream_t alt_stream = nullptr;   // when set, launches go here instead of the main stream
   cudaStream_t user_stream = nullptr;
   bool use_user_stream = false;
   cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ov_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // overlap_scales: input ready, blur[0..1] written, blur[0..1] consumed
   uint64_t launches = 0;
   bool use_async = true;   // cp.async software-pipelined Gaussian passes (option "async_passes")
   bool use_box = true;     // masked paths smooth only the mask's support box (option "support_box")
   int* box_host = nullptr; // pinned: the mask extents come back here once per call
+  bool overlap_scales = false;   // option "overlap_scales": features of scale s run beside the passes of scale s+1
   std::string error;
   ife::Workspace ws;
   // optional per-kernel timing (ife_cuda_profile_*): event pairs around every launch
@@ -76,5 +80,6 @@ struct ife_cuda_ctx {
   int n_ranks = 1;
   int rank = 0;
 
-  cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
+  cudaStream_t main_stream() const { return use_user_stream ? user_stream : own_stream; }
+  cudaStream_t stream() const { return alt_stream ? alt_stream : main_stream(); }
 };

@@ -555,6 +555,12 @@ int ife_cuda_create(int device, ife_cuda_ctx** out) {
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   for (auto& ev : ctx->events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (auto& ev : ctx->ov_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    cudaStreamCreateWithPriority(&ctx->hp_stream, cudaStreamNonBlocking, greatest);
+  }
   *out = ctx;
   return IFE_OK;
 }
@@ -567,6 +573,8 @@ void ife_cuda_destroy(ife_cuda_ctx* ctx) {
   ctx->ws.release_all();
   if (ctx->box_host) cudaFreeHost(ctx->box_host);
   for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ov_events) if (ev) cudaEventDestroy(ev);
+  if (ctx->hp_stream) cudaStreamDestroy(ctx->hp_stream);
   for (auto& ev : ctx->prof_events) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -608,6 +616,7 @@ int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return IFE_E_INVALID;
   if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
   if (std::strcmp(name, "support_box") == 0) { ctx->use_box = value != 0; return IFE_OK; }
+  if (std::strcmp(name, "overlap_scales") == 0) { ctx->overlap_scales = value != 0; return IFE_OK; }
   return fail(ctx, IFE_E_INVALID, "unknown option '%s'", name);
 }
 
@@ -807,19 +816,40 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
   int box[6];         // all eight outputs are masked: smooth only what in-mask voxels can see
   bool have_box;
   IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, nullptr, 0, box, &have_box));
+  // Option "overlap_scales" (device-resident calls with several scales): the Gaussian passes run
+  // on the context's high-priority stream one scale ahead of the fused feature kernel, which
+  // stays on the main stream and fills the issue slots the FP64-latency-bound passes leave
+  // idle; two blur buffers, events ov_events[1+b] (blur b written) / [3+b] (blur b consumed).
+  const bool overlap = ctx->overlap_scales && mem == IFE_MEM_DEVICE && n_sigma > 1 && ctx->hp_stream;
+  if (overlap) {
+    IFE_TRY(ctx->ws.blur2.reserve(ctx, n * sizeof(float)));
+    IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->ov_events[0], ctx->main_stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->hp_stream, ctx->ov_events[0], 0));
+  }
   for (int s = 0; s < n_sigma; ++s) {
-    float* blur = (float*)ctx->ws.blur.ptr;
+    float* blur = (float*)(overlap && (s & 1) ? ctx->ws.blur2.ptr : ctx->ws.blur.ptr);
     float* d_out = mem == IFE_MEM_HOST ? (float*)ctx->ws.out[s & 1].ptr : out + (size_t)s * 8 * n;
     if (mem == IFE_MEM_HOST && s >= 2)  // the staging buffer must have been drained
       IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream(), ctx->events[2 + (s & 1)], 0));
-    IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                          nullptr, nullptr, have_box ? box : nullptr));
+    if (overlap) {
+      if (s >= 2) IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->hp_stream, ctx->ov_events[3 + (s & 1)], 0));
+      ctx->alt_stream = ctx->hp_stream;
+    }
+    const int rc_smooth = smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
+                                        nullptr, nullptr, have_box ? box : nullptr);
+    ctx->alt_stream = nullptr;
+    IFE_TRY(rc_smooth);
+    if (overlap) {
+      IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->ov_events[1 + (s & 1)], ctx->hp_stream));
+      IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->main_stream(), ctx->ov_events[1 + (s & 1)], 0));
+    }
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
     A.vol = blur; A.mask_u8 = d_mask;
     for (int k = 0; k < 8; ++k) A.out[k] = d_out + (size_t)k * n;
     A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
     IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+    if (overlap) IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->ov_events[3 + (s & 1)], ctx->main_stream()));
     if (mem == IFE_MEM_HOST) {
       IFE_CUDA_TRY(ctx, cudaEventRecord(ctx->events[s & 1], ctx->stream()));
       IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[s & 1], 0));

@@ -96,7 +96,11 @@ uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx);
  * voxel can see -- the mask's bounding box (clipped to the ROI list's, when there is one)
  * grown by the one-voxel stencil reach; the box is reduced on the device and read back once
  * per call, which makes these calls wait for the stream once.  0 smooths the whole volume
- * (same results bit for bit). */
+ * (same results bit for bit).
+ * "overlap_scales" (default 0): device-resident ife_cuda_emphysema_features calls with several
+ * scales run the Gaussian passes one scale ahead on a high-priority stream of the context,
+ * beside the fused feature kernel of the scale before (two blur buffers); same results bit
+ * for bit, +2..4 % throughput measured, per-kernel timings then overlap. */
 int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value);
 
 /* Optional per-kernel timing for benchmarks: while enabled, every kernel launch of the

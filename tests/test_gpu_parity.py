@@ -257,6 +257,32 @@ def test_support_box_is_invisible(ctx, oracle):
     assert np.array_equal(both[1], ctx.emphysema_histograms(img, corner, sigmas, edges))
 
 
+def test_overlap_scales_same_results(ctx):
+    """Option overlap_scales (device-resident calls): the Gaussian passes run one scale ahead
+    on a second stream, the feature kernel of the scale before beside them, two blur buffers
+    and events in between.  Same bits as the serial schedule, call after call."""
+    torch = pytest.importorskip("torch")
+    shape = (40, 64, 96)
+    sigmas = [0.6, 1.2, 2.4, 4.8, 1.0]
+    img = torch.from_numpy(synth.ct_like(shape, seed=41, n_blobs=10)).cuda()
+    mask = torch.from_numpy(synth.clamp01(synth.lung_mask(shape))).cuda()
+    dims = (shape[2], shape[1], shape[0])
+    ref = torch.empty((len(sigmas), 8) + shape, dtype=torch.float32, device="cuda")
+    out = torch.full_like(ref, float("nan"))
+    torch.cuda.synchronize()          # the context runs on its own (non-blocking) stream
+    ctx.emphysema_features_dev(img.data_ptr(), mask.data_ptr(), ref.data_ptr(), dims, sigmas)
+    ctx.synchronize()
+    ctx.set_option("overlap_scales", 1)
+    try:
+        for _ in range(3):     # back to back: the second call must not overtake the first one's readers
+            ctx.emphysema_features_dev(img.data_ptr(), mask.data_ptr(), out.data_ptr(), dims, sigmas)
+        ctx.synchronize()
+    finally:
+        ctx.set_option("overlap_scales", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), ref.view(torch.int32))
+
+
 # ------------------------------------------------------------------------------ histograms
 def test_histogram_flat_array(ctx, oracle):
     import os
