@@ -240,6 +240,11 @@ def test_support_box_is_invisible(ctx, oracle):
         assert mismatch_report(out[s, :2], ref[:2])[0] == 0
         assert_eigen_parity(np.moveaxis(out[s, 2:], 0, -1), np.moveaxis(ref[2:], 0, -1), "box sigma=%g" % sigma)
     assert np.all(ctx.emphysema_features(img, np.zeros(shape, np.uint8), sigmas) == 0)
+    ctx.set_option("async_passes", 0)         # the plain pass kernels take the same windows
+    try:
+        assert bits_equal(ctx.emphysema_features(img, corner, sigmas), out)
+    finally:
+        ctx.set_option("async_passes", 1)
     # histograms: the box is also clipped to the ROI list's bounding box
     edges = _edges_for(oracle, img, blob, sigmas, 12)
     rois = np.array([[60, 12, 22, 9, 7, 5], [72, 20, 26, 11, 9, 6]], np.int32)   # x,y,z,sx,sy,sz
