@@ -154,10 +154,21 @@ StencilCoef make_stencil_coef(const double spacing[3]) {
 // Recursive Gaussian passes
 // ---------------------------------------------------------------------------------------
 constexpr int kChunk = 16;
-constexpr int kXWarps = 4;
+#ifndef IFE_CHUNK_S
+#define IFE_CHUNK_S 16     // chunk length of the pipelined strided (y / z) passes
+#endif
+#ifndef IFE_MINB_S
+#define IFE_MINB_S 3
+#endif
+constexpr int kChunkS = IFE_CHUNK_S;
+#ifndef IFE_XWARPS
+#define IFE_XWARPS 4
+#endif
+constexpr int kXWarps = IFE_XWARPS;
 
 size_t ckpt_bytes(int nf, int n, size_t n_lines) {
-  const int n_chunks = (n + kChunk - 1) / kChunk;
+  constexpr int kc = kChunkS < kChunk ? kChunkS : kChunk;
+  const int n_chunks = (n + kc - 1) / kc;
   return (size_t)std::max(n_chunks - 1, 0) * nf * 4 * n_lines * sizeof(double);
 }
 
@@ -177,10 +188,10 @@ int launch_strided_async_m(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs
   // (uint8 mask input) with the replay buffer in registers, 3 stages, 2 CTAs/SM (0.67 vs 0.71).
   constexpr bool YBS = NF == 2;
   constexpr int STAGES = YBS ? 2 : kAsyncStages;
-  constexpr int MINB = YBS ? 3 : 1;
-  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, MASKMODE, kChunk, FMA, STAGES, YBS, MINB>;
-  const size_t smem = sizeof(AsyncStage<NF, INMODE, kChunk, !YBS>) * STAGES +
-                      (YBS ? (size_t)NF * kChunk * kAsyncThreads * sizeof(double) : 0);
+  constexpr int MINB = YBS ? IFE_MINB_S : 1;
+  auto kern = gauss_pass_strided_async<NF, INMODE, DIVIDE, MASKMODE, kChunkS, FMA, STAGES, YBS, MINB>;
+  const size_t smem = sizeof(AsyncStage<NF, INMODE, kChunkS, !YBS>) * STAGES +
+                      (YBS ? (size_t)NF * kChunkS * kAsyncThreads * sizeof(double) : 0);
   IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A.n_lines + kAsyncThreads - 1) / kAsyncThreads);
   kern<<<grid, kAsyncThreads, smem, ctx->stream()>>>(C, A);

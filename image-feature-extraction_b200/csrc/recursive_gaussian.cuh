@@ -473,7 +473,10 @@ gauss_pass_strided(const __grid_constant__ GaussCoef C, const __grid_constant__ 
 // register-staged kernel runs).
 // ---------------------------------------------------------------------------------------
 constexpr int kAsyncThreads = 128;
-constexpr int kYbsUnroll = 4;
+#ifndef IFE_YBS_UNROLL
+#define IFE_YBS_UNROLL 4
+#endif
+constexpr int kYbsUnroll = IFE_YBS_UNROLL;
 
 template <int NF, int INMODE, int L, bool CK = true>
 struct AsyncStage {
