@@ -463,6 +463,14 @@ def test_full_size_invariants_512x512x400(ctx):
            b[z + 1, y, x] - 6.0 * b[z, y, x])
     if inside[z - 1:z + 2, y - 1:y + 2, x - 1:x + 2].all():
         assert abs(out[5][z, y, x] - lap) <= 1e-3 * max(1.0, abs(lap))
+    # the support box (on by default) changes nothing at full size either
+    ctx.set_option("support_box", 0)
+    try:
+        full = ctx.emphysema_features(img, mask, [1.2])[0]
+    finally:
+        ctx.set_option("support_box", 1)
+    assert bits_equal(out, full)
+    del full
     # histograms of the same run: row sums == number of in-mask voxels
     edges = np.stack([synth.equalized_edges(out[k][inside][::97], 40) for k in range(8)])
     counts = ctx.emphysema_histograms(img, mask, [1.2], edges)
