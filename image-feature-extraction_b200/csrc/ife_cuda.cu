@@ -230,8 +230,11 @@ int launch_strided(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
 
 template <int NF, bool FMA>
 int launch_x_async(ife_cuda_ctx* ctx, const GaussCoef& C, const PassArgs& A) {
-  auto kern = gauss_pass_x_async<NF, kChunk, FMA, kXWarps, kAsyncStages>;
-  const size_t smem = kXWarps * (kAsyncStages * sizeof(XStage<NF, kChunk>) + sizeof(XOut<NF, kChunk>));
+#ifndef IFE_X_STAGES
+#define IFE_X_STAGES kAsyncStages
+#endif
+  auto kern = gauss_pass_x_async<NF, kChunk, FMA, kXWarps, IFE_X_STAGES>;
+  const size_t smem = kXWarps * (IFE_X_STAGES * sizeof(XStage<NF, kChunk>) + sizeof(XOut<NF, kChunk>));
   IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long lines_per_block = 32LL * kXWarps;
   const unsigned grid = (unsigned)((A.n_lines + lines_per_block - 1) / lines_per_block);

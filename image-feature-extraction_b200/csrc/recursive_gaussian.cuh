@@ -1012,8 +1012,11 @@ __device__ __forceinline__ void xstage_read(const XStage<NF, L>& S, int lane, fl
     }
 }
 
+#ifndef IFE_X_MINB
+#define IFE_X_MINB 1     // experiment hook: resident CTAs the x pass's registers are cut for
+#endif
 template <int NF, int L, bool FMA, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, IFE_X_MINB)
 gauss_pass_x_async(const __grid_constant__ GaussCoef C, const __grid_constant__ PassArgs A) {
   extern __shared__ __align__(16) unsigned char xasync_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
