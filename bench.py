@@ -4,6 +4,7 @@ features, 512^2 x 400 CT; % HBM peak).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
                   [--workload extract|hist|slab] [--mask ones|lung] [--arith fma|plain]
+                  [--rois N] [--no-box] [--overlap] [--no-e2e] [--no-cpu-baseline]
 
 One "step" = one pass of the hot path over one synthetic scan: ImageToEmphysemaFeaturesFilter
 semantics (masked normalized convolution -> gradient magnitude -> fused Hessian/eigen
@@ -11,7 +12,11 @@ features -> mask) at sigma in {0.6, 1.2, 2.4, 4.8}, eight float feature volumes 
 scale (tools/ExtractFeatures.cxx semantics, BASELINE.json configs[1]).  Units = voxel-scales
 (nx*ny*nz*|sigma|).  N > 1: one process per GPU (torchrun), one scan per GPU, no data-path
 collective (weak scaling); `--workload slab` instead cuts ONE volume into z-slabs with NCCL
-halo exchange (configs[3]).
+halo exchange (configs[3]).  `--workload hist` bins the features into DenseHistograms instead of
+writing them (MakeBag semantics, configs[2] and [4]; `--rois N` bins into N fixed-seed 41^3
+ROIs); `--mask lung` uses the lung-shaped mask of SURVEY.md section 8d, where the support box
+(`--no-box` turns it off) cuts the smoothing work.  The default stays the
+all-ones mask: nothing can be skipped.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max
 over ranks); `e2e` goes through the C ABI with pinned HOST buffers, H2D and D2H inside the
