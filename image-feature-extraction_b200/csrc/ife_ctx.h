@@ -29,9 +29,10 @@ struct Workspace {
   DeviceBuffer packed;          // eight bin indices per voxel (many-ROI histogram path)
   DeviceBuffer slab_img, slab_mask;  // slab + halo planes (multi-GPU)
   DeviceBuffer box;             // raw extents[6] of the output mask (support_box.cuh)
+  DeviceBuffer crop_img, crop_mask, crop_blur;   // the mask's bounding box as a dense volume (smooth_masked)
   void release_all() {
     DeviceBuffer* all[] = {&a0, &a1, &b0, &b1, &blur, &ckpt, &in_img, &in_mask, &out[0], &out[1],
-                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box, &blur2};
+                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box, &blur2, &crop_img, &crop_mask, &crop_blur};
     for (DeviceBuffer* b : all) b->release();
   }
 };

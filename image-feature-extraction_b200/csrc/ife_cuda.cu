@@ -408,6 +408,97 @@ int compute_support_box(ife_cuda_ctx* ctx, const uint8_t* d_mask, int nx, int ny
   return IFE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Masked smoothing.  With a mask c in {0, != 0} both fields of the normalized convolution, c*T
+// and c, are EXACT zeros outside the mask's bounding box.  The recursion of a line that has
+// only seen zeros is in the zero state, and ITK's boundary rule (the first sample extended to
+// infinity) starts a line whose first sample is zero in that same state.  So smoothing the
+// bounding box grown by one voxel as if it were the whole image -- a dense copy of it -- gives
+// the same bits inside it as smoothing the whole image, for all three passes, at a cost
+// proportional to the box instead of the volume.  (Where the box touches the image border
+// the first sample is the image's own: the same rule either way.)  An ROI list shrinks what
+// is needed further but not what is zero: there the box of the mask is cropped and the
+// ROI-clipped box windows the passes inside the crop (smooth_volume's `box`).
+// ---------------------------------------------------------------------------------------
+struct MaskedPlan {
+  bool have_box = false;   // the support box is known (else: smooth everything)
+  bool empty = false;      // no voxel is wanted
+  bool cropped = false;    // the passes run on a cropped copy
+  int box[6];              // wanted region, full coordinates (ROI-clipped, grown by one voxel)
+  int org[3], cdim[3];     // crop origin / size
+  int cbox[6];             // `box` in crop coordinates
+  bool window = false;     // cbox is much smaller than the crop: window the passes with it
+  const float* img = nullptr;      // what the passes read: the cropped copies or the caller's
+  const uint8_t* mask = nullptr;
+};
+
+// widen [lo, hi) to at least 4 samples inside [0, n)
+inline void widen4(int& lo, int& hi, int n) {
+  while (hi - lo < 4 && hi < n) ++hi;
+  while (hi - lo < 4 && lo > 0) --lo;
+}
+
+// After the extents of slot `slot` are on the host.  Launches the crop on the context's stream.
+int plan_masked(ife_cuda_ctx* ctx, bool have_box, int slot, const float* d_img, const uint8_t* d_mask,
+                int nx, int ny, int nz, const int* rois, int n_roi, MaskedPlan* P) {
+  *P = MaskedPlan();
+  P->img = d_img; P->mask = d_mask;
+  P->have_box = have_box;
+  if (!have_box) return IFE_OK;
+  int mbox[6];
+  finish_support_box(ctx, slot, nx, ny, nz, nullptr, 0, mbox);
+  finish_support_box(ctx, slot, nx, ny, nz, rois, n_roi, P->box);
+  P->empty = P->box[0] >= P->box[1];
+  if (P->empty) return IFE_OK;
+  if (nx % 32 != 0 || reinterpret_cast<uintptr_t>(d_img) % 16 != 0) return IFE_OK;
+  int lo[3] = {mbox[0] / 32 * 32, mbox[2], mbox[4]};
+  int hi[3] = {std::min(nx, (mbox[1] + 31) / 32 * 32), mbox[3], mbox[5]};
+  widen4(lo[1], hi[1], ny);
+  widen4(lo[2], hi[2], nz);
+  const long long nc = (long long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  if ((double)nc > 0.85 * (double)nx * ny * nz) return IFE_OK;   // not worth the copy
+  for (int d = 0; d < 3; ++d) { P->org[d] = lo[d]; P->cdim[d] = hi[d] - lo[d]; }
+  for (int d = 0; d < 3; ++d) {
+    P->cbox[2 * d] = std::max(P->box[2 * d] - lo[d], 0);
+    P->cbox[2 * d + 1] = std::min(P->box[2 * d + 1] - lo[d], P->cdim[d]);
+  }
+  const long long nb = (long long)(P->cbox[1] - P->cbox[0]) * (P->cbox[3] - P->cbox[2]) * (P->cbox[5] - P->cbox[4]);
+  P->window = n_roi > 0 && (double)nb < 0.8 * (double)nc;
+  Workspace& ws = ctx->ws;
+  IFE_TRY(ws.crop_img.reserve(ctx, (size_t)nc * sizeof(float)));
+  IFE_TRY(ws.crop_mask.reserve(ctx, (size_t)nc));
+  IFE_TRY(ws.crop_blur.reserve(ctx, (size_t)nc * sizeof(float)));
+  const long long n4 = nc / 4;
+  const unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 16LL * ctx->sm_count);
+  crop_box_kernel<<<grid, 256, 0, ctx->stream()>>>(d_img, d_mask, (float*)ws.crop_img.ptr, (uint8_t*)ws.crop_mask.ptr,
+                                                   nx, ny, lo[0], lo[1], lo[2], P->cdim[0], P->cdim[1], n4);
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  P->cropped = true;
+  P->img = (const float*)ws.crop_img.ptr;
+  P->mask = (const uint8_t*)ws.crop_mask.ptr;
+  return IFE_OK;
+}
+
+// blur (full layout) <- normalized Gaussian of (img, mask) at `sigma`, valid wherever P.box says
+int smooth_masked(ife_cuda_ctx* ctx, const MaskedPlan& P, const float* d_img, const uint8_t* d_mask,
+                  float* blur, int nx, int ny, int nz, const double spacing[3], double sigma) {
+  if (P.have_box && P.empty) return IFE_OK;
+  if (!P.cropped)
+    return smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigma, nullptr, nullptr,
+                         P.have_box ? P.box : nullptr);
+  float* cblur = (float*)ctx->ws.crop_blur.ptr;
+  IFE_TRY(smooth_volume(ctx, P.img, P.mask, true, cblur, P.cdim[0], P.cdim[1], P.cdim[2], 0, P.cdim[2], spacing,
+                        sigma, nullptr, nullptr, P.window ? P.cbox : nullptr));
+  const long long n4 = (long long)P.cdim[0] * P.cdim[1] * P.cdim[2] / 4;
+  const unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 16LL * ctx->sm_count);
+  uncrop_kernel<<<grid, 256, 0, ctx->stream()>>>(cblur, blur, nx, ny, P.org[0], P.org[1], P.org[2], P.cdim[0],
+                                                 P.cdim[1], n4);
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
 int reserve_smoothing(ife_cuda_ctx* ctx, int nf, int nx, int ny, int nzb) {
   Workspace& ws = ctx->ws;
   const size_t vol = (size_t)nx * ny * nzb * sizeof(float);
@@ -830,6 +921,8 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
   int box[6];         // all eight outputs are masked: smooth only what in-mask voxels can see
   bool have_box;
   IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, nullptr, 0, box, &have_box));
+  MaskedPlan plan;
+  IFE_TRY(plan_masked(ctx, have_box, 0, d_img, d_mask, nx, ny, nz, nullptr, 0, &plan));
   // Option "overlap_scales" (device-resident calls with several scales): the Gaussian passes run
   // on the context's high-priority stream one scale ahead of the fused feature kernel, which
   // stays on the main stream and fills the issue slots the FP64-latency-bound passes leave
@@ -849,8 +942,7 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
       if (s >= 2) IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->hp_stream, ctx->ov_events[3 + (s & 1)], 0));
       ctx->alt_stream = ctx->hp_stream;
     }
-    const int rc_smooth = smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                                        nullptr, nullptr, have_box ? box : nullptr);
+    const int rc_smooth = smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s]);
     ctx->alt_stream = nullptr;
     IFE_TRY(rc_smooth);
     if (overlap) {
@@ -935,10 +1027,11 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
   int box[6];         // only in-mask voxels (inside some ROI, when there are ROIs) are binned
   bool have_box;
   IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, rois, n_roi, box, &have_box));
+  MaskedPlan plan;
+  IFE_TRY(plan_masked(ctx, have_box, 0, d_img, d_mask, nx, ny, nz, rois, n_roi, &plan));
   for (int s = 0; s < n_sigma; ++s) {
     float* blur = (float*)ctx->ws.blur.ptr;
-    IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                          nullptr, nullptr, have_box ? box : nullptr));
+    IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s]));
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
     A.vol = blur; A.mask_u8 = d_mask;
@@ -1036,16 +1129,13 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
     const uint8_t* d_mask = (const uint8_t*)mask_slot[k]->ptr;
     uint32_t* d_counts = (uint32_t*)ws.counts.ptr + (size_t)k * n_counts;
     IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), st));
-    int box[6];
-    const bool have_box = use_box;
-    if (use_box) {
-      IFE_CUDA_TRY(ctx, cudaEventSynchronize(ctx->events[k]));   // upload i and its box are in
-      finish_support_box(ctx, k, nx, ny, nz, n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr, n_roi, box);
-    }
+    if (use_box) IFE_CUDA_TRY(ctx, cudaEventSynchronize(ctx->events[k]));   // upload i and its box are in
+    MaskedPlan plan;
+    IFE_TRY(plan_masked(ctx, use_box, k, d_img, d_mask, nx, ny, nz,
+                        n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr, n_roi, &plan));
     for (int s = 0; s < n_sigma; ++s) {
       float* blur = (float*)ws.blur.ptr;
-      IFE_TRY(smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigmas[s],
-                            nullptr, nullptr, have_box ? box : nullptr));
+      IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s]));
       FeatArgs A;
       std::memset(&A, 0, sizeof(A));
       A.vol = blur; A.mask_u8 = d_mask;

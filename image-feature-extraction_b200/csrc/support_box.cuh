@@ -70,4 +70,35 @@ mask_box_kernel(const uint8_t* __restrict__ mask, int nx, int ny, unsigned n_row
   }
 }
 
+
+// Crop / un-crop between the full volume and the box [o, o + c) (x origin and extent multiples
+// of 4, rows 16-byte aligned): four voxels per thread.  See smooth_masked in ife_cuda.cu: the
+// masked smoothing runs on the cropped copy, because everything outside the mask's bounding
+// box is an exact zero for the recursion.
+__global__ void __launch_bounds__(256)
+crop_box_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, float* __restrict__ cimg,
+                uint8_t* __restrict__ cmask, int nx, int ny, int ox, int oy, int oz, int cx, int cy,
+                long long n4) {
+  const int cx4 = cx >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cx4;
+    const int x4 = (int)(i - r * cx4), y = (int)(r % cy), z = (int)(r / cy);
+    const size_t src = ((size_t)(z + oz) * ny + (size_t)(y + oy)) * nx + (size_t)(ox + 4 * x4);
+    reinterpret_cast<float4*>(cimg)[i] = __ldg(reinterpret_cast<const float4*>(img + src));
+    reinterpret_cast<uchar4*>(cmask)[i] = __ldg(reinterpret_cast<const uchar4*>(mask + src));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+uncrop_kernel(const float* __restrict__ cvol, float* __restrict__ vol, int nx, int ny, int ox, int oy, int oz,
+              int cx, int cy, long long n4) {
+  const int cx4 = cx >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cx4;
+    const int x4 = (int)(i - r * cx4), y = (int)(r % cy), z = (int)(r / cy);
+    const size_t dst = ((size_t)(z + oz) * ny + (size_t)(y + oy)) * nx + (size_t)(ox + 4 * x4);
+    *reinterpret_cast<float4*>(vol + dst) = __ldg(reinterpret_cast<const float4*>(cvol) + i);
+  }
+}
+
 }  // namespace ife
