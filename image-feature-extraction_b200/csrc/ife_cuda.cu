@@ -480,9 +480,31 @@ int plan_masked(ife_cuda_ctx* ctx, bool have_box, int slot, const float* d_img, 
   return IFE_OK;
 }
 
+// ROI list in crop coordinates, clipped to the crop (in-mask voxels all lie inside it)
+std::vector<int> rois_in_crop(const MaskedPlan& P, const int* rois, int n_roi) {
+  std::vector<int> r((size_t)n_roi * 6);
+  for (int i = 0; i < n_roi; ++i) {
+    int lo[3], hi[3];
+    bool empty = false;
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::max(rois[6 * i + d] - P.org[d], 0);
+      hi[d] = std::min(rois[6 * i + d] + rois[6 * i + 3 + d] - P.org[d], P.cdim[d]);
+      empty = empty || lo[d] >= hi[d];
+    }
+    for (int d = 0; d < 3; ++d) {
+      r[6 * i + d] = empty ? 0 : lo[d];
+      r[6 * i + 3 + d] = empty ? 0 : hi[d] - lo[d];
+    }
+  }
+  return r;
+}
+
 // blur (full layout) <- normalized Gaussian of (img, mask) at `sigma`, valid wherever P.box says
+// (uncrop = false: the result stays in ws.crop_blur, crop layout -- histogram-only callers run the
+// fused kernel on the crop as well)
 int smooth_masked(ife_cuda_ctx* ctx, const MaskedPlan& P, const float* d_img, const uint8_t* d_mask,
-                  float* blur, int nx, int ny, int nz, const double spacing[3], double sigma) {
+                  float* blur, int nx, int ny, int nz, const double spacing[3], double sigma,
+                  bool uncrop = true) {
   if (P.have_box && P.empty) return IFE_OK;
   if (!P.cropped)
     return smooth_volume(ctx, d_img, d_mask, true, blur, nx, ny, nz, 0, nz, spacing, sigma, nullptr, nullptr,
@@ -490,6 +512,7 @@ int smooth_masked(ife_cuda_ctx* ctx, const MaskedPlan& P, const float* d_img, co
   float* cblur = (float*)ctx->ws.crop_blur.ptr;
   IFE_TRY(smooth_volume(ctx, P.img, P.mask, true, cblur, P.cdim[0], P.cdim[1], P.cdim[2], 0, P.cdim[2], spacing,
                         sigma, nullptr, nullptr, P.window ? P.cbox : nullptr));
+  if (!uncrop) return IFE_OK;
   const long long n4 = (long long)P.cdim[0] * P.cdim[1] * P.cdim[2] / 4;
   const unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 16LL * ctx->sm_count);
   uncrop_kernel<<<grid, 256, 0, ctx->stream()>>>(cblur, blur, nx, ny, P.org[0], P.org[1], P.org[2], P.cdim[0],
@@ -1004,10 +1027,8 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
   IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.edges.ptr, edges, (size_t)rows * n_edges * sizeof(float),
                                     cudaMemcpyHostToDevice, ctx->stream()));
   const int* d_rois = nullptr;
-  if (n_roi > 0) {
+  if (n_roi > 0) {   // uploaded below, once the crop frame is known
     IFE_TRY(ctx->ws.rois.reserve(ctx, (size_t)n_roi * 6 * sizeof(int)));
-    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.rois.ptr, rois, (size_t)n_roi * 6 * sizeof(int),
-                                      cudaMemcpyHostToDevice, ctx->stream()));
     d_rois = (const int*)ctx->ws.rois.ptr;
   }
   uint32_t* d_counts = counts;
@@ -1029,13 +1050,23 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
   IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, rois, n_roi, box, &have_box));
   MaskedPlan plan;
   IFE_TRY(plan_masked(ctx, have_box, 0, d_img, d_mask, nx, ny, nz, rois, n_roi, &plan));
-  for (int s = 0; s < n_sigma; ++s) {
-    float* blur = (float*)ctx->ws.blur.ptr;
-    IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s]));
+  // no feature volume leaves this call, so with a crop the fused kernel runs on the crop too
+  // (its dims, its copy of the mask, the ROI list moved into its frame)
+  const int fx = plan.cropped ? plan.cdim[0] : nx, fy = plan.cropped ? plan.cdim[1] : ny,
+            fz = plan.cropped ? plan.cdim[2] : nz;
+  if (n_roi > 0) {
+    const std::vector<int> moved = plan.cropped ? rois_in_crop(plan, rois, n_roi) : std::vector<int>();
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.rois.ptr, plan.cropped ? moved.data() : rois,
+                                      (size_t)n_roi * 6 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream()));
+    if (plan.cropped) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));   // `moved` is about to go
+  }
+  for (int s = 0; s < n_sigma && !(plan.have_box && plan.empty); ++s) {
+    float* blur = plan.cropped ? (float*)ctx->ws.crop_blur.ptr : (float*)ctx->ws.blur.ptr;
+    IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s], false));
     FeatArgs A;
     std::memset(&A, 0, sizeof(A));
-    A.vol = blur; A.mask_u8 = d_mask;
-    A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
+    A.vol = blur; A.mask_u8 = plan.mask;
+    A.nx = fx; A.ny = fy; A.nzb = fz; A.zb0 = 0; A.zb1 = fz;
     A.hist.edges = (const float*)ctx->ws.edges.ptr + (size_t)s * 8 * n_edges;
     A.hist.counts = d_counts + (size_t)s * 8 * nb;
     A.hist.n_edges = n_edges;
@@ -1045,7 +1076,7 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
       IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
       ProfScope prof(ctx, K_OTHER);
       roi_hist_packed_kernel<<<(unsigned)n_roi, 256, (size_t)8 * nb * sizeof(uint32_t), ctx->stream()>>>(
-          A.hist.packed, nx, ny, d_rois, nb, A.hist.counts, A.hist.stride_roi);
+          A.hist.packed, fx, fy, d_rois, nb, A.hist.counts, A.hist.stride_roi);
       ctx->launches++;
       IFE_CUDA_TRY(ctx, cudaGetLastError());
     } else {
@@ -1121,6 +1152,7 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
   };
   IFE_TRY(upload(0));
   const StencilCoef S = make_stencil_coef(spacing);
+  std::vector<std::vector<int>> moved((size_t)n_scans);   // alive until the copies have run
   for (int i = 0; i < n_scans; ++i) {
     const int k = i & 1;
     if (i + 1 < n_scans) IFE_TRY(upload(i + 1));
@@ -1131,15 +1163,22 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
     IFE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, n_counts * sizeof(uint32_t), st));
     if (use_box) IFE_CUDA_TRY(ctx, cudaEventSynchronize(ctx->events[k]));   // upload i and its box are in
     MaskedPlan plan;
-    IFE_TRY(plan_masked(ctx, use_box, k, d_img, d_mask, nx, ny, nz,
-                        n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr, n_roi, &plan));
-    for (int s = 0; s < n_sigma; ++s) {
-      float* blur = (float*)ws.blur.ptr;
-      IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s]));
+    const int* scan_rois = n_roi > 0 ? rois + (size_t)i * n_roi * 6 : nullptr;
+    IFE_TRY(plan_masked(ctx, use_box, k, d_img, d_mask, nx, ny, nz, scan_rois, n_roi, &plan));
+    const int fx = plan.cropped ? plan.cdim[0] : nx, fy = plan.cropped ? plan.cdim[1] : ny,
+              fz = plan.cropped ? plan.cdim[2] : nz;
+    if (plan.cropped && n_roi > 0) {   // this scan's ROIs in the frame of its crop
+      moved[i] = rois_in_crop(plan, scan_rois, n_roi);
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync((int*)ws.rois.ptr + (size_t)i * n_roi * 6, moved[i].data(),
+                                        (size_t)n_roi * 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    for (int s = 0; s < n_sigma && !(plan.have_box && plan.empty); ++s) {
+      float* blur = plan.cropped ? (float*)ws.crop_blur.ptr : (float*)ws.blur.ptr;
+      IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s], false));
       FeatArgs A;
       std::memset(&A, 0, sizeof(A));
-      A.vol = blur; A.mask_u8 = d_mask;
-      A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
+      A.vol = blur; A.mask_u8 = plan.mask;
+      A.nx = fx; A.ny = fy; A.nzb = fz; A.zb0 = 0; A.zb1 = fz;
       A.hist.edges = (const float*)ws.edges.ptr + (size_t)s * 8 * n_edges;
       A.hist.counts = d_counts + (size_t)s * 8 * nb;
       A.hist.rois = n_roi > 0 ? (const int*)ws.rois.ptr + (size_t)i * n_roi * 6 : nullptr;

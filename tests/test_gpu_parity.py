@@ -280,6 +280,19 @@ def test_support_box_is_invisible(ctx, oracle):
             ctx.set_option("support_box", 1)
         assert np.array_equal(got, full)
     assert got.sum() > 0
+    many = synth.dense_rois(blob, (7, 5, 3))[::3]          # > 192 ROIs: packed-bin path, on the crop
+    assert len(many) > 192
+    got = ctx.emphysema_histograms(img, blob, sigmas, edges, many)
+    ctx.set_option("support_box", 0)
+    try:
+        full = ctx.emphysema_histograms(img, blob, sigmas, edges, many)
+    finally:
+        ctx.set_option("support_box", 1)
+    assert np.array_equal(got, full) and got.sum() > 0
+    roisb = np.stack([rois, rois + np.array([3, 2, 1, 0, 0, 0], np.int32)])
+    bothr = ctx.emphysema_histograms_batch([img, img], [blob, blob], sigmas, edges, roisb)
+    assert np.array_equal(bothr[0], ctx.emphysema_histograms(img, blob, sigmas, edges, roisb[0]))
+    assert np.array_equal(bothr[1], ctx.emphysema_histograms(img, blob, sigmas, edges, roisb[1]))
     both = ctx.emphysema_histograms_batch([img, img], [blob, corner], sigmas, edges)
     assert np.array_equal(both[0], ctx.emphysema_histograms(img, blob, sigmas, edges))
     assert np.array_equal(both[1], ctx.emphysema_histograms(img, corner, sigmas, edges))
