@@ -93,10 +93,11 @@ uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx);
  * results bit for bit; kept as the fallback for layouts the pipelined kernels reject).
  * "support_box" (default 1): the calls whose every result is masked
  * (ife_cuda_emphysema_features / _histograms / _histograms_batch) smooth only what an in-mask
- * voxel can see -- the mask's bounding box (clipped to the ROI list's, when there is one)
- * grown by the one-voxel stencil reach; the box is reduced on the device and read back once
- * per call, which makes these calls wait for the stream once.  0 smooths the whole volume
- * (same results bit for bit).
+ * voxel can see -- the mask's bounding box grown by the one-voxel stencil reach, smoothed as a
+ * dense cropped copy (outside the mask both fields of the normalized convolution are exact
+ * zeros, so the crop gives the same bits), and inside it only the ROI list's bounding box when
+ * there is one; the box is reduced on the device and read back once per call, which makes
+ * these calls wait for the stream once.  0 smooths the whole volume (same results bit for bit).
  * "overlap_scales" (default 0): device-resident ife_cuda_emphysema_features calls with several
  * scales run the Gaussian passes one scale ahead on a high-priority stream of the context,
  * beside the fused feature kernel of the scale before (two blur buffers); same results bit
