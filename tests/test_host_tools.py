@@ -99,7 +99,7 @@ def test_tools_end_to_end_against_oracle(tmp_path, oracle):
 def test_makebag_against_oracle(tmp_path, oracle):
     """tools/MakeBag.cxx semantics: ROI file in, one CSV row of 8*|scales| histograms'
     frequencies per ROI out; and the random-ROI mode writes a .ROIInfo that reads back."""
-    shape = (30, 34, 38)
+    shape = (30, 34, 64)      # nx % 32 == 0: the tool goes through the cropped masked smoothing
     img = synth.ct_like(shape, seed=61, n_blobs=8)
     lab = synth.lung_mask(shape).astype(np.uint16)
     m01 = synth.clamp01(lab.astype(np.uint8))
