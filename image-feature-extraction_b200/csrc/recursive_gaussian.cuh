@@ -477,6 +477,12 @@ constexpr int kAsyncThreads = 128;
 #define IFE_YBS_UNROLL 4
 #endif
 constexpr int kYbsUnroll = IFE_YBS_UNROLL;
+// boundary (first / last / partial) chunks of the strided passes: rolled loops; unrolling by the
+// recursion order makes the state rotation free there too
+#ifndef IFE_GEN_UNROLL
+#define IFE_GEN_UNROLL 1
+#endif
+constexpr int kGenUnroll = IFE_GEN_UNROLL;
 
 template <int NF, int INMODE, int L, bool CK = true>
 struct AsyncStage {
@@ -678,7 +684,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     }
     auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
     if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false, YBS ? kYbsUnroll : L>(C, src, i0, len, cs);
-    else forward_chunk<NF, L, FMA, true, YBS ? 1 : L>(C, src, i0, len, cs);
+    else forward_chunk<NF, L, FMA, true, YBS ? kGenUnroll : L>(C, src, i0, len, cs);
     if (k == n_chunks - 1) {  // the line's last sample is the anticausal edge value
       double v[NF];
       stage_sample<NF, INMODE, L, !YBS>(S, 3 + len - 1, t, v);
@@ -791,7 +797,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
       // samples and replay buffer are both in shared memory: the loops need no register arrays
       // and can stay partially rolled (smaller code, fewer instruction-cache misses)
       if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false, kYbsUnroll>(C, src, sink, i0, len, n, cs, as, ybs);
-      else backward_chunk<NF, L, FMA, true, 1>(C, src, sink, i0, len, n, cs, as, ybs);
+      else backward_chunk<NF, L, FMA, true, kGenUnroll>(C, src, sink, i0, len, n, cs, as, ybs);
     } else {
       if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);
       else backward_chunk<NF, L, FMA, true>(C, src, sink, i0, len, n, cs, as);
