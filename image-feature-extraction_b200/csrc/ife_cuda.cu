@@ -432,10 +432,14 @@ struct MaskedPlan {
   const uint8_t* mask = nullptr;
 };
 
-// widen [lo, hi) to at least 4 samples inside [0, n)
+// widen [lo, hi) to at least 4 samples inside [0, n) and, where there is room, to a multiple
+// of the chunk length (whole chunks at both ends of a line take the interleaved loop); the
+// added samples are zeros like everything else outside the mask's box
 inline void widen4(int& lo, int& hi, int n) {
   while (hi - lo < 4 && hi < n) ++hi;
   while (hi - lo < 4 && lo > 0) --lo;
+  while ((hi - lo) % kChunk != 0 && hi < n) ++hi;
+  while ((hi - lo) % kChunk != 0 && lo > 0) --lo;
 }
 
 // After the extents of slot `slot` are on the host.  Launches the crop on the context's stream.

@@ -131,10 +131,31 @@ __device__ __forceinline__ size_t ckpt_index(int chunk, int f, int k, size_t n_l
 // the recurrence.  GENERIC = true handles the first chunk (boundary coefficients), the
 // last chunk(s) and partial chunks.
 // ---------------------------------------------------------------------------------------
-template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, typename SRC>
+// EDGE (hot path only, GENERIC = false): bit 0 = the chunk starts the line (its first four
+// causal samples take the boundary coefficients, chosen at compile time), bit 1 = the chunk
+// ends the line (likewise its last four anticausal samples).  The chunk must be full.
+template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, int EDGE = 0, typename SRC>
 __device__ __forceinline__ void forward_chunk(const GaussCoef& C, const SRC& src, int i0, int len,
                                               Rec (&cs)[NF]) {
   Fb fb = fb_select(C.D, C.BN, 4);
+  if (!GENERIC && (EDGE & 1)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Fb fe = fb_select(C.D, C.BN, j);
+      double v[NF];
+      src(j, v);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) causal_step<FMA>(C, fe, cs[f], v[f]);
+    }
+#pragma unroll UNROLL
+    for (int j = 4; j < L; ++j) {
+      double v[NF];
+      src(j, v);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) causal_step<FMA>(C, fb, cs[f], v[f]);
+    }
+    return;
+  }
 #pragma unroll UNROLL
   for (int j = 0; j < L; ++j) {
     if (!GENERIC || j < len) {
@@ -163,7 +184,7 @@ struct SmemYB {
   __device__ __forceinline__ double get(int f, int j) const { return col[(f * L + j) * THREADS]; }
 };
 
-template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, typename SRC, typename SINK, typename YB>
+template <int NF, int L, bool FMA, bool GENERIC, int UNROLL = L, int EDGE = 0, typename SRC, typename SINK, typename YB>
 __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& src, const SINK& sink,
                                                int i0, int len, int n, Rec (&cs)[NF],
                                                Rec (&as)[NF], YB& yb) {
@@ -179,8 +200,28 @@ __device__ __forceinline__ void backward_chunk(const GaussCoef& C, const SRC& sr
     const Fb fc = fb_select(C.D, C.BN, 4);
     const Fb fa = fb_select(C.D, C.BM, 4);
     constexpr int U2 = UNROLL >= L ? L / 2 : UNROLL;
+    constexpr int T0 = EDGE != 0 ? 4 : 0;
+    if (EDGE != 0) {
+      // a chunk at the start / end of the line: the four samples that still see the virtual
+      // constant extension sit in the first four steps (causal j = t, anticausal j = L-1-t)
+      static_assert(EDGE == 0 || L / 2 >= 4, "edge steps must fall into the first half");
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int jc = t, ja = L - 1 - t;
+        const Fb fce = (EDGE & 1) ? fb_select(C.D, C.BN, t) : fc;
+        const Fb fae = (EDGE & 2) ? fb_select(C.D, C.BM, t) : fa;
+        double vc[NF], va[NF];
+        src(jc, vc);
+        src(ja, va);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          yb.set(f, jc, causal_step<FMA>(C, fce, cs[f], vc[f]));
+          yb.set(f, ja, anti_step<FMA>(C, fae, as[f], va[f]));
+        }
+      }
+    }
 #pragma unroll U2
-    for (int t = 0; t < L / 2; ++t) {
+    for (int t = T0; t < L / 2; ++t) {
       const int jc = t, ja = L - 1 - t;
       double vc[NF], va[NF];
       src(jc, vc);
@@ -483,6 +524,11 @@ constexpr int kYbsUnroll = IFE_YBS_UNROLL;
 #define IFE_GEN_UNROLL 1
 #endif
 constexpr int kGenUnroll = IFE_GEN_UNROLL;
+// full chunks at the start / end of a line take the interleaved hot loop with compile-time
+// boundary coefficients instead of the rolled generic loops (strided passes, two fields)
+#ifndef IFE_EDGE_HOT
+#define IFE_EDGE_HOT 1
+#endif
 
 template <int NF, int INMODE, int L, bool CK = true>
 struct AsyncStage {
@@ -684,6 +730,7 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
     }
     auto src = [&](int j, double (&v)[NF]) { stage_sample<NF, INMODE, L, !YBS>(S, 3 + j, t, v); };
     if (len == L && i0 >= 4) forward_chunk<NF, L, FMA, false, YBS ? kYbsUnroll : L>(C, src, i0, len, cs);
+    else if (IFE_EDGE_HOT && YBS && len == L && i0 == 0) forward_chunk<NF, L, FMA, false, kYbsUnroll, 1>(C, src, i0, len, cs);
     else forward_chunk<NF, L, FMA, true, YBS ? kGenUnroll : L>(C, src, i0, len, cs);
     if (k == n_chunks - 1) {  // the line's last sample is the anticausal edge value
       double v[NF];
@@ -797,6 +844,8 @@ gauss_pass_strided_async(const __grid_constant__ GaussCoef C, const __grid_const
       // samples and replay buffer are both in shared memory: the loops need no register arrays
       // and can stay partially rolled (smaller code, fewer instruction-cache misses)
       if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false, kYbsUnroll>(C, src, sink, i0, len, n, cs, as, ybs);
+      else if (IFE_EDGE_HOT && len == L && i0 == 0 && n >= 2 * L) backward_chunk<NF, L, FMA, false, kYbsUnroll, 1>(C, src, sink, i0, len, n, cs, as, ybs);
+      else if (IFE_EDGE_HOT && len == L && i0 + L == n && i0 >= L) backward_chunk<NF, L, FMA, false, kYbsUnroll, 2>(C, src, sink, i0, len, n, cs, as, ybs);
       else backward_chunk<NF, L, FMA, true, kGenUnroll>(C, src, sink, i0, len, n, cs, as, ybs);
     } else {
       if (chunk_is_interior<L>(i0, len, n)) backward_chunk<NF, L, FMA, false>(C, src, sink, i0, len, n, cs, as);

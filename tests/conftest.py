@@ -24,6 +24,10 @@ def oracle():
 @pytest.fixture(scope="session")
 def ctx():
     """One device context for the whole GPU session (fails loudly without a GPU)."""
+    try:                      # torch first: its bundled NCCL must be the one in the process when
+        import torch          # a later test imports torch after the library has dlopen'ed NCCL
+    except ImportError:
+        pass
     import ife_b200
     c = ife_b200.Context(0)
     yield c
