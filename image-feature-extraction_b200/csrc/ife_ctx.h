@@ -40,7 +40,7 @@ struct Workspace {
 int fail(ife_cuda_ctx* ctx, int code, const char* fmt, ...);
 
 // kernel kinds for ife_cuda_profile_read
-enum { K_PASS_Z = 0, K_PASS_X = 1, K_PASS_Y = 2, K_FEATURES = 3, K_OTHER = 4, K_NUM = 5 };
+enum { K_PASS_Z = 0, K_PASS_X = 1, K_PASS_Y = 2, K_FEATURES = 3, K_OTHER = 4, K_EXCHANGE = 5, K_NUM = 6 };
 
 // RAII: records a CUDA event before and after a kernel launch when profiling is on
 struct ProfScope {
@@ -80,6 +80,8 @@ struct ife_cuda_ctx {
   void* nccl_comm = nullptr;
   int n_ranks = 1;
   int rank = 0;
+  // what the last masked call's passes actually ran on (the crop of the mask's box, or the volume)
+  int work_dims[3] = {0, 0, 0};
 
   cudaStream_t main_stream() const { return use_user_stream ? user_stream : own_stream; }
   cudaStream_t stream() const { return alt_stream ? alt_stream : main_stream(); }

@@ -68,7 +68,12 @@ ProfScope::~ProfScope() {
 int DeviceBuffer::reserve(ife_cuda_ctx* ctx, size_t want) {
   if (want <= bytes) return IFE_OK;
   if (ptr) {
-    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+    // every stream of the context may still be reading the old allocation (copy stream: D2H of
+    // the previous scale / halo exchange; high-priority stream: option overlap_scales)
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->main_stream()));
+    if (ctx->alt_stream) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->alt_stream));
+    if (ctx->copy_stream) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->hp_stream) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->hp_stream));
     IFE_CUDA_TRY(ctx, cudaFree(ptr));
     ptr = nullptr;
     bytes = 0;
@@ -448,6 +453,7 @@ int plan_masked(ife_cuda_ctx* ctx, bool have_box, int slot, const float* d_img, 
   *P = MaskedPlan();
   P->img = d_img; P->mask = d_mask;
   P->have_box = have_box;
+  ctx->work_dims[0] = nx; ctx->work_dims[1] = ny; ctx->work_dims[2] = nz;
   if (!have_box) return IFE_OK;
   int mbox[6];
   finish_support_box(ctx, slot, nx, ny, nz, nullptr, 0, mbox);
@@ -479,6 +485,7 @@ int plan_masked(ife_cuda_ctx* ctx, bool have_box, int slot, const float* d_img, 
   ctx->launches++;
   IFE_CUDA_TRY(ctx, cudaGetLastError());
   P->cropped = true;
+  for (int d = 0; d < 3; ++d) ctx->work_dims[d] = P->cdim[d];
   P->img = (const float*)ws.crop_img.ptr;
   P->mask = (const uint8_t*)ws.crop_mask.ptr;
   return IFE_OK;
@@ -743,6 +750,12 @@ int ife_cuda_synchronize(ife_cuda_ctx* ctx) {
 }
 
 uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ife_cuda_last_work_dims(const ife_cuda_ctx* ctx, int dims[3]) {
+  if (!ctx || !dims) return IFE_E_INVALID;
+  for (int d = 0; d < 3; ++d) dims[d] = ctx->work_dims[d];
+  return IFE_OK;
+}
 
 int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return IFE_E_INVALID;

@@ -344,13 +344,17 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
       IFE_CUDA_TRY(ctx, cudaEventRecord(ev_far, cs));
       far_ready = ev_far;
     }
-    IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_near, 0));
+    {
+      // profiling kind 5: how long the main stream sits in this wait = the exposed part of the
+      // first exchange group (the second group hides behind the kernels of the first scale)
+      ProfScope prof(ctx, K_EXCHANGE);
+      IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_near, 0));
+    }
   }
 
   uint32_t* d_counts = nullptr;
   IFE_TRY(slab_compute(ctx, bimg, bmask, bz0, bz1, z0, z1, out, global_dims, spacing, sigmas, n_sigma,
                        edges, n_edges, counts, halo_factor, mem, &d_counts, far_ready, near_h));
-  IFE_CUDA_TRY(ctx, cudaEventRecord(ev_done, st));
 
   // ---- combine the per-rank histograms ----
   if (edges) {
@@ -361,6 +365,10 @@ int ife_cuda_slab_emphysema_features(ife_cuda_ctx* ctx, const float* image_slab,
       IFE_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, n_counts * sizeof(uint32_t),
                                         cudaMemcpyDeviceToHost, st));
   }
+  // recorded AFTER the all-reduce: the next call's exchange (copy stream) waits on it, so the
+  // communicator never has operations in flight on two streams at once, and the halo planes are
+  // not overwritten while this call's kernels still read them
+  IFE_CUDA_TRY(ctx, cudaEventRecord(ev_done, st));
   if (mem == IFE_MEM_HOST) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return IFE_OK;
 }

@@ -60,6 +60,7 @@ def load_library():
     L.ife_cuda_reserve.argtypes = [vp, ip, i]
     L.ife_cuda_launch_count.argtypes = [vp]
     L.ife_cuda_launch_count.restype = C.c_uint64
+    L.ife_cuda_last_work_dims.argtypes = [vp, ip]
     L.ife_cuda_set_option.argtypes = [vp, C.c_char_p, i]
     L.ife_cuda_profile_enable.argtypes = [vp, i]
     L.ife_cuda_profile_read.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
@@ -179,15 +180,22 @@ class Context:
     def launch_count(self):
         return int(self.L.ife_cuda_launch_count(self.h))
 
-    PROFILE_KINDS = ["gauss_pass_z", "gauss_pass_x", "gauss_pass_y", "features_fused", "other"]
+    def last_work_dims(self):
+        """(nx, ny, nz) the Gaussian passes of the last masked call ran on (crop or full volume)."""
+        d = (C.c_int * 3)()
+        self._check(self.L.ife_cuda_last_work_dims(self.h, d))
+        return tuple(int(v) for v in d)
+
+    PROFILE_KINDS = ["gauss_pass_z", "gauss_pass_x", "gauss_pass_y", "features_fused", "other",
+                     "exchange_wait"]
 
     def profile_enable(self, on=True):
         self._check(self.L.ife_cuda_profile_enable(self.h, int(on)))
 
     def profile_read(self):
         """-> {kind: (total_ms, launches)} since the last read (synchronises)."""
-        ms = (C.c_double * 5)()
-        n = (C.c_uint64 * 5)()
+        ms = (C.c_double * len(self.PROFILE_KINDS))()
+        n = (C.c_uint64 * len(self.PROFILE_KINDS))()
         self._check(self.L.ife_cuda_profile_read(self.h, ms, n))
         return {k: (ms[j], int(n[j])) for j, k in enumerate(self.PROFILE_KINDS)}
 

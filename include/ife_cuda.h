@@ -87,6 +87,11 @@ int ife_cuda_synchronize(ife_cuda_ctx* ctx);
 int ife_cuda_reserve(ife_cuda_ctx* ctx, const int dims[3], int n_outputs);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t ife_cuda_launch_count(const ife_cuda_ctx* ctx);
+/* Dimensions of the volume the Gaussian passes of the last masked call
+ * (ife_cuda_emphysema_features / _histograms / _histograms_batch) actually ran on: the dense crop
+ * of the mask's support box (option "support_box"), or the full dims when no crop was taken.
+ * For benchmarks that report bytes moved per kernel. */
+int ife_cuda_last_work_dims(const ife_cuda_ctx* ctx, int dims[3]);
 
 /* Tuning / debugging switches.  "async_passes" (default 1): use the cp.async software-
  * pipelined Gaussian pass kernels; 0 selects the plain register-staged kernels (same
@@ -108,8 +113,10 @@ int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value);
  * context is bracketed by CUDA events on the launching stream.  ife_cuda_profile_read
  * synchronises, returns the summed device time (ms) and launch count per kernel kind since
  * the last read, and resets.  Kinds: 0 = Gaussian z pass, 1 = x pass, 2 = y pass,
- * 3 = fused Hessian/eigen/feature(/histogram) kernel, 4 = other. */
-#define IFE_PROFILE_KINDS 5
+ * 3 = fused Hessian/eigen/feature(/histogram) kernel, 4 = other, 5 = not a kernel: the time
+ * the main stream of ife_cuda_slab_emphysema_features waited for the first halo exchange group
+ * (the exposed part of the exchange). */
+#define IFE_PROFILE_KINDS 6
 int ife_cuda_profile_enable(ife_cuda_ctx* ctx, int on);
 int ife_cuda_profile_read(ife_cuda_ctx* ctx, double ms[IFE_PROFILE_KINDS],
                           uint64_t launches[IFE_PROFILE_KINDS]);

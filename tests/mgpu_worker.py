@@ -43,8 +43,37 @@ def main():
         stats = torch.tensor([float(neq.sum()), float(np.abs(out.astype(np.float64) - ref)[neq].max() if neq.any() else 0.0),
                               float(np.abs(counts.astype(np.int64) - whole_counts).sum())], dtype=torch.float64)
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        # north_star terms: voxels whose eigenvalues differ by more than 1e-4 * max|lambda|
+        lam, lam_ref = out[:, 2:5].astype(np.float64), ref[:, 2:5].astype(np.float64)
+        scale = np.abs(lam_ref).max(1)
+        rel = np.where(scale > 0, np.abs(lam - lam_ref).max(1) / np.where(scale > 0, scale, 1), 0.0)
+        bad = torch.tensor([float((rel > 1e-4).sum()), float(rel.size)], dtype=torch.float64)
+        dist.all_reduce(bad, op=dist.ReduceOp.SUM)
         res[name] = {"max_mismatching_values_per_rank": stats[0].item(), "max_abs_diff": stats[1].item(),
-                     "hist_abs_diff_vs_whole": stats[2].item(), "values_per_rank": int(out.size)}
+                     "hist_abs_diff_vs_whole": stats[2].item(), "values_per_rank": int(out.size),
+                     "frac_voxels_eig_err_gt_1e-4": bad[0].item() / bad[1].item(),
+                     "hist_inserts": int(whole_counts.sum())}
+        if name == "full_halo":
+            # two device-mode calls with histograms back to back, no synchronisation in between:
+            # the second call's halo exchange (copy stream) must order itself behind the first
+            # call's all-reduce (main stream) -- one communicator, never two streams at once
+            dev = torch.device("cuda", local)
+            d_img = torch.from_numpy(img[z0:z1].copy()).to(dev)
+            d_mask = torch.from_numpy(mask[z0:z1].copy()).to(dev)
+            d_out = [torch.empty((2, 8) + d_img.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            d_cnt = [torch.zeros(counts.shape, dtype=torch.int32, device=dev) for _ in range(2)]
+            torch.cuda.synchronize()
+            for it in range(2):
+                ctx.slab_emphysema_features_dev(d_img.data_ptr(), d_mask.data_ptr(), d_out[it].data_ptr(),
+                                                (shape[2], shape[1], nz), sigmas, edges=edges,
+                                                counts_ptr=d_cnt[it].data_ptr(), halo_factor=hf)
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            ok = all(np.array_equal(d_out[it].cpu().numpy(), out, equal_nan=True) and
+                     np.array_equal(d_cnt[it].cpu().numpy().astype(np.int64), counts.astype(np.int64)) for it in range(2))
+            okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            res["back_to_back_device_calls_equal_host_call"] = bool(okt.item() == 1.0)
     ctx.comm_destroy()
     ctx.close()
     if rank == 0:

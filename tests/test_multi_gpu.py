@@ -29,7 +29,11 @@ def test_nccl_slab_path_two_gpus():
     print(res)
     assert res["full_halo"]["max_mismatching_values_per_rank"] == 0      # bit-identical to one GPU
     assert res["full_halo"]["hist_abs_diff_vs_whole"] == 0
-    assert res["default_halo"]["max_abs_diff"] < 1.0
+    assert res["back_to_back_device_calls_equal_host_call"]
+    # default halo (12 sigma + 5 planes): an approximation with a stated bound (include/ife_cuda.h)
+    assert res["default_halo"]["frac_voxels_eig_err_gt_1e-4"] < 1e-3
+    assert res["default_halo"]["max_abs_diff"] < 0.05
+    assert res["default_halo"]["hist_abs_diff_vs_whole"] <= 2e-4 * res["default_halo"]["hist_inserts"]
 
 
 def _gloo_worker(rank, world, port, shape, sigma, halo, q):
