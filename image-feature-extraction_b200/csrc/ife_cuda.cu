@@ -17,6 +17,7 @@
 #include "eigen_features.cuh"
 #include "features_march.cuh"
 #include "recursive_gaussian.cuh"
+#include "iir_tma.cuh"
 #include "support_box.cuh"
 #include "ife_ctx.h"
 
@@ -178,10 +179,85 @@ size_t ckpt_bytes(int nf, int n, size_t n_lines) {
 }
 
 size_t ckpt_bytes_volume(int nf, int nx, int ny, int nz) {
-  const size_t a = ckpt_bytes(nf, nz, (size_t)nx * ny);
-  const size_t b = ckpt_bytes(nf, nx, (size_t)ny * nz);
-  const size_t c = ckpt_bytes(nf, ny, (size_t)nx * nz);
+  // lines padded to whole tiles of 32 (the tensor-map kernels checkpoint every lane of a tile)
+  const size_t px = (size_t)(nx + 31) / 32 * 32, py = (size_t)(ny + 31) / 32 * 32;
+  const size_t a = ckpt_bytes(nf, nz, px * ny);
+  const size_t b = ckpt_bytes(nf, nx, py * nz);
+  const size_t c = ckpt_bytes(nf, ny, px * nz);
   return std::max(a, std::max(b, c));
+}
+
+// ---------------------------------------------------------------------------------------
+// Tensor-map (TMA) passes: iir_tma.cuh.  cuTensorMapEncodeTiled comes from the driver through
+// the runtime's entry-point query, so the library does not link libcuda.
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 3-D view, x fastest: dims in elements, strides of dims 1 and 2 in bytes
+int make_map3(ife_cuda_ctx* ctx, CUtensorMap* m, const void* base, bool u8, long long d0, long long d1, long long d2,
+              long long stride1_bytes, long long stride2_bytes, int b0, int b1, int b2, bool swizzle64) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(ctx, IFE_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  const cuuint64_t strides[2] = {(cuuint64_t)stride1_bytes, (cuuint64_t)stride2_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = fn(m, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                        const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, IFE_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return IFE_OK;
+}
+
+#ifndef IFE_TMA_MINB_S
+#define IFE_TMA_MINB_S 12    // resident 64-thread blocks per SM the strided passes' registers are cut for
+#endif
+#ifndef IFE_TMA_MINB_X
+#define IFE_TMA_MINB_X 9
+#endif
+
+template <int AXIS, int INMODE, bool DIVIDE>
+int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0, const CUtensorMap& i1,
+                    const CUtensorMap& o0, const CUtensorMap& o1, const TmaArgs& A, dim3 grid) {
+  constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X : IFE_TMA_MINB_S;
+  constexpr size_t smem = (INMODE == IN_IMG_U8 ? kRegionImgU8 + kRegionU8 : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) +
+                          kTmaBarBytes;
+  if (ctx->arith == IFE_ARITH_FMA) {
+    auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, true, MINB>;
+    IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 64, smem, ctx->stream()>>>(C, i0, i1, o0, o1, A);
+  } else {
+    auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, false, MINB>;
+    IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 64, smem, ctx->stream()>>>(C, i0, i1, o0, o1, A);
+  }
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
+// Can the two-field smoothing of an nx x ny x nzb volume take the tensor-map kernels?
+bool tma_passes_usable(const ife_cuda_ctx* ctx, const float* in0, const void* cert, bool cert_is_u8, const float* out0,
+                       int nx, int ny, int nzb, const uint8_t* outmask_u8, const float* outmask_f32) {
+  if (!ctx->use_tma || !cert || !cert_is_u8 || outmask_u8 || outmask_f32) return false;
+  if (nx % 16 != 0 || ny >= 65536 || nzb >= 65536) return false;   // 16-byte row pitch of the uint8 mask; grid.y
+  auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  return al(in0) && al(cert) && al(out0) && encode_tiled_fn() != nullptr;
 }
 
 constexpr int kAsyncStages = 3;
@@ -306,6 +382,52 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
   float* a1 = (float*)ws.a1.ptr;
   float* b0 = (float*)ws.b0.ptr;
   float* b1 = (float*)ws.b1.ptr;
+
+  if (tma_passes_usable(ctx, in0, cert, cert_is_u8, out0, nx, ny, nzb, outmask_u8, outmask_f32)) {
+    // tensor-map staged passes (iir_tma.cuh): same windows, same results bit for bit
+    const long long plane = (long long)nx * ny;
+    const int nzk = kz1 - kz0;
+    const size_t koff = (size_t)kz0 * plane, boff = (size_t)(kz0 - keep0) * plane;
+    CUtensorMap mi0, mi1, mo0, mo1;
+    TmaArgs T;
+    std::memset(&T, 0, sizeof(T));
+    T.ckpt = (double*)ws.ckpt.ptr;
+    {   // z pass: lanes along x, block y = row, samples along z; the multiply c*T is fused into the loads
+      IFE_TRY(make_map3(ctx, &mi0, in0, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTRows, false));
+      IFE_TRY(make_map3(ctx, &mi1, cert, true, nx, ny, nzb, nx, plane, 32, 1, kTRows, false));
+      IFE_TRY(make_map3(ctx, &mo0, a0, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
+      IFE_TRY(make_map3(ctx, &mo1, a1, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
+      T.in0 = in0; T.in1 = cert;
+      T.s_lane = 1; T.s_bx = 32; T.s_by = nx; T.s_n = plane; T.lanes_total = nx;
+      T.n = nzb; T.out_lo = kz0; T.out_hi = kz1;
+      ProfScope prof(ctx, K_PASS_Z);
+      IFE_TRY((launch_tma_pass<AX_Z, IN_IMG_U8, false>(ctx, cz, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, ny))));
+    }
+    {   // x pass: lanes along y (one line each), block y = plane, samples along x
+      IFE_TRY(make_map3(ctx, &mi0, a0 + koff, false, nx, ny, nzk, 4LL * nx, 4 * plane, kXRow, 32, 1, false));
+      IFE_TRY(make_map3(ctx, &mi1, a1 + koff, false, nx, ny, nzk, 4LL * nx, 4 * plane, kXRow, 32, 1, false));
+      IFE_TRY(make_map3(ctx, &mo0, b0 + boff, false, nx, ny, nzk, 4LL * nx, 4 * plane, kTL, 32, 1, true));
+      IFE_TRY(make_map3(ctx, &mo1, b1 + boff, false, nx, ny, nzk, 4LL * nx, 4 * plane, kTL, 32, 1, true));
+      T.in0 = a0 + koff; T.in1 = a1 + koff;
+      T.s_lane = nx; T.s_bx = 32LL * nx; T.s_by = plane; T.s_n = 1; T.lanes_total = ny;
+      T.n = nx; T.out_lo = 0; T.out_hi = nx;
+      ProfScope prof(ctx, K_PASS_X);
+      IFE_TRY((launch_tma_pass<AX_X, IN_FIELDS, false>(ctx, cx, mi0, mi1, mo0, mo1, T, dim3((ny + 31) / 32, nzk))));
+    }
+    {   // y pass: lanes along x in [kx0, kx1), block y = plane, samples along y; the divide is fused into the stores
+      const size_t yoff = boff + (size_t)kx0;
+      const int wx = kx1 - kx0;
+      IFE_TRY(make_map3(ctx, &mi0, b0 + yoff, false, wx, ny, nzk, 4LL * nx, 4 * plane, 32, kTRows, 1, false));
+      IFE_TRY(make_map3(ctx, &mi1, b1 + yoff, false, wx, ny, nzk, 4LL * nx, 4 * plane, 32, kTRows, 1, false));
+      IFE_TRY(make_map3(ctx, &mo0, out0 + yoff, false, wx, ny, nzk, 4LL * nx, 4 * plane, 32, kTL, 1, false));
+      T.in0 = b0 + yoff; T.in1 = b1 + yoff;
+      T.s_lane = 1; T.s_bx = 32; T.s_by = plane; T.s_n = nx; T.lanes_total = wx;
+      T.n = ny; T.out_lo = ky0; T.out_hi = ky1;
+      ProfScope prof(ctx, K_PASS_Y);
+      IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, true>(ctx, cy, mi0, mi1, mo0, mo0, T, dim3((wx + 31) / 32, nzk))));
+    }
+    return IFE_OK;
+  }
 
   PassArgs A;
   std::memset(&A, 0, sizeof(A));
@@ -760,6 +882,7 @@ int ife_cuda_last_work_dims(const ife_cuda_ctx* ctx, int dims[3]) {
 int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return IFE_E_INVALID;
   if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
+  if (std::strcmp(name, "tma_passes") == 0) { ctx->use_tma = value != 0; return IFE_OK; }
   if (std::strcmp(name, "support_box") == 0) { ctx->use_box = value != 0; return IFE_OK; }
   if (std::strcmp(name, "overlap_scales") == 0) { ctx->overlap_scales = value != 0; return IFE_OK; }
   return fail(ctx, IFE_E_INVALID, "unknown option '%s'", name);

@@ -77,7 +77,7 @@ int main() {
   float* din;
   cudaMalloc(&din, 64 * 128 * 4);
   cudaMemset(din, 0, 64 * 128 * 4);
-  for (int b : {1, 2, 3, 4}) {
+  for (int b : {1, 2, 3, 4, 5, 6, 8}) {
     run<1>(b, p.multiProcessorCount, khz / 1000.0, din);
     run<2>(b, p.multiProcessorCount, khz / 1000.0, din);
     run<4>(b, p.multiProcessorCount, khz / 1000.0, din);

@@ -125,6 +125,42 @@ def test_normalized_gaussian_bit_exact(ctx, oracle, arith):
     assert mismatch_report(out_fm, np.where(cert != 0, ref_f, np.float32(0)))[0] == 0
 
 
+@pytest.mark.parametrize("arith", [0, 1])
+def test_tensor_map_passes_bit_exact(ctx, oracle, arith):
+    """The tensor-map staged, field-per-warp passes (csrc/iir_tma.cuh; taken when nx % 16 == 0
+    with a uint8 certainty) against the cp.async passes and the oracle: whole tiles, ragged
+    tiles in every direction (nx, ny not multiples of 32, lines that are not whole chunks),
+    lines shorter than one chunk, the smallest volume ITK accepts."""
+    shapes = [((40, 64, 96), 1.2), ((37, 45, 48), 2.4), ((4, 4, 16), 0.6), ((5, 6, 32), 1.0),
+              ((16, 16, 16), 4.8), ((33, 32, 64), 0.6), ((19, 70, 80), 1.0), ((130, 20, 16), 4.8)]
+    ctx.set_arith(arith)
+    try:
+        for shape, sigma in shapes:      # shape = (nz, ny, nx)
+            img = synth.ct_like(shape, seed=sum(shape), n_blobs=6)
+            m8 = synth.clamp01(synth.lung_mask(shape))
+            if min(shape) < 8:
+                m8 = (np.random.default_rng(3).uniform(0, 1, shape) < 0.7).astype(np.uint8)
+            got = ctx.normalized_gaussian(img, m8, sigma)
+            ctx.set_option("tma_passes", 0)
+            try:
+                old = ctx.normalized_gaussian(img, m8, sigma)
+            finally:
+                ctx.set_option("tma_passes", 1)
+            n, worst = mismatch_report(got, old)
+            assert n == 0, "%s sigma=%g: %d values differ from the cp.async passes (max %g)" % (shape, sigma, n, worst)
+            if np.prod(shape) < 200_000:
+                ref = oracle.normalized_gaussian(img, m8.astype(np.float32), sigma, arith=arith)
+                assert mismatch_report(got, ref)[0] == 0, "%s sigma=%g vs oracle" % (shape, sigma)
+        # mask values other than 0/1 (the filter casts, it does not clamp)
+        shape = (24, 40, 64)
+        img = synth.ct_like(shape, seed=5, n_blobs=5)
+        m8 = np.random.default_rng(4).integers(0, 4, shape).astype(np.uint8)
+        got = ctx.normalized_gaussian(img, m8, 1.5)
+        assert mismatch_report(got, oracle.normalized_gaussian(img, m8.astype(np.float32), 1.5, arith=arith))[0] == 0
+    finally:
+        ctx.set_arith(1)
+
+
 def test_normalized_gaussian_zero_divisor_rule(ctx, oracle):
     # certainty identically zero -> G(c) == 0 -> itk::DivideImageFilter yields float max
     img = synth.ct_like((8, 8, 8), seed=1, n_blobs=2)
