@@ -227,6 +227,9 @@ int make_map3(ife_cuda_ctx* ctx, CUtensorMap* m, const void* base, bool u8, long
 #ifndef IFE_TMA_MINB_S
 #define IFE_TMA_MINB_S 12    // resident 64-thread blocks per SM the strided passes' registers are cut for
 #endif
+#ifndef IFE_TMA_MINB_Z
+#define IFE_TMA_MINB_Z 11    // z pass: 20.2 KB of shared memory per block (two roles + the tile of ones)
+#endif
 #ifndef IFE_TMA_MINB_X
 #define IFE_TMA_MINB_X 9
 #endif
@@ -234,9 +237,9 @@ int make_map3(ife_cuda_ctx* ctx, CUtensorMap* m, const void* base, bool u8, long
 template <int AXIS, int INMODE, bool DIVIDE>
 int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0, const CUtensorMap& i1,
                     const CUtensorMap& o0, const CUtensorMap& o1, const TmaArgs& A, dim3 grid) {
-  constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X : IFE_TMA_MINB_S;
-  constexpr size_t smem = (INMODE == IN_IMG_U8 ? kRegionImgU8 + kRegionU8 : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) +
-                          kTmaBarBytes;
+  constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X : (INMODE == IN_IMG_U8 ? IFE_TMA_MINB_Z : IFE_TMA_MINB_S);
+  constexpr size_t smem = (INMODE == IN_IMG_U8 ? kRegionImgU8 + kRegionU8 + kOnesTile
+                                               : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) + kTmaBarBytes;
   if (ctx->arith == IFE_ARITH_FMA) {
     auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, true, MINB>;
     IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
