@@ -200,6 +200,7 @@ def equalized_edges_from_scan(torch, ctx, img, mask, n_edges, dims=None):
         for k in range(8):
             v = torch.sort(feats[0, k].reshape(-1)[pick].to(torch.float64)).values
             rows.append(v[(q * (v.numel() - 1)).long()].to(torch.float32))
+        torch.cuda.synchronize()   # torch's stream has read `feats` before the library (own stream) overwrites it
     del feats
     edges = torch.stack(rows).cpu().numpy()
     # strictly increasing rows keep every bin meaningful even where a feature saturates
@@ -680,6 +681,10 @@ def leg_slab(env):
     sub = min(64, size)
     edges = equalized_edges_from_scan(torch, ctx, full[:sub].contiguous(), full_mask[:sub].contiguous(), N_EDGES,
                                       dims=(size, size, sub))
+    if world > 1:   # one set of edges for every rank (MakeBag reads them from one file): rank 0's
+        box = [edges if rank == 0 else None]
+        env.dist.broadcast_object_list(box, src=0)
+        edges = box[0]
     rows, nb = len(SIGMAS) * 8, N_EDGES + 1
     per_scale = 8 * n_own * 4 * len(SIGMAS) > 60e9    # one scale's outputs at a time when all four would not fit
     out = torch.empty(((1 if per_scale else len(SIGMAS)), 8, nzo, size, size), dtype=torch.float32, device=dev)

@@ -61,7 +61,8 @@ __device__ __forceinline__ unsigned opaque_u32(unsigned v) {
   return v;
 }
 
-// MODE / HIST / UNIT as in features_kernel.  HIST here is the whole-volume
+// MODE / HIST / UNIT as in features_kernel; MODE 3 (this kernel only) = the six Hessian entries
+// themselves, no eigen solve.  HIST here is the whole-volume
 // histogram only (A.hist.n_roi == 0); ROI lists stay with the brick kernel, whose culling of
 // bricks that touch no ROI is worth more than the march.  Masks: uint8 or none.
 // OUTS: 1 = every output plane pointer is set, 2 = none is (histograms only), 0 = test each
@@ -69,7 +70,7 @@ template <int MODE, bool HIST, bool UNIT, int OUTS>
 __global__ void __launch_bounds__(kMX * kMY, HIST ? IFE_MARCH_MINB_HIST : IFE_MARCH_MINB)
 features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_constant__ FeatArgs A,
                       const int zchunk) {
-  constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
+  constexpr int NFEAT = MODE == 0 ? 8 : ((MODE == 1 || MODE == 3) ? 6 : 1);
   constexpr int NT = kMX * kMY;
   __shared__ float plane[4][kMPlane];   // ring: plane pz+2 lands while plane pz is consumed
   __shared__ __align__(16) unsigned char s_mask[4][kMX * kMY];   // the mask bytes of the same planes
@@ -193,7 +194,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
     N.Dy = deriv1<UNIT>(S.d1[1], ym, yp);
     if (N.inside) {
       const double dxm = (double)xm, dxp = (double)xp, dym = (double)ym, dyp = (double)yp;
-      if (MODE == 0 || MODE == 1) {
+      if (MODE == 0 || MODE == 1 || MODE == 3) {
         N.Dxx = deriv2<UNIT>(S.d2a[0], S.d2b[0], dxm, N.cD, dxp);
         N.Dyy = deriv2<UNIT>(S.d2a[1], S.d2b[1], dym, N.cD, dyp);
         const float dx_ym = deriv1<UNIT>(S.d1[0], pl[lc - kMPX - 1], pl[lc - kMPX + 1]);
@@ -234,7 +235,7 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
           }
           if (MODE == 0) { f[0] = C.c; f[1] = gm; } else f[0] = gm;
         }
-        if (MODE == 0 || MODE == 1) {
+        if (MODE == 0 || MODE == 1 || MODE == 3) {
           float H[6], e[6];
           H[0] = C.Dxx;
           H[1] = C.Dxy;
@@ -246,7 +247,12 @@ features_march_kernel(const __grid_constant__ StencilCoef S, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 6; ++k) e[k] = H[k];
 #else
-          eigen_features6_lean(H, e);
+          if (MODE == 3) {   // itk::Hessian3DImageFilter's own output: [Dxx, Dxy, Dxz, Dyy, Dyz, Dzz] (.hxx:53-59)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) e[k] = H[k];
+          } else {
+            eigen_features6_lean(H, e);
+          }
 #endif
           constexpr int o6 = MODE == 0 ? 2 : 0;
 #pragma unroll

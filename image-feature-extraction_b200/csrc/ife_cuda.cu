@@ -677,7 +677,7 @@ int reserve_smoothing(ife_cuda_ctx* ctx, int nf, int nx, int ny, int nzb) {
 template <int MODE, bool HIST>
 void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                        const StencilCoef& S, const FeatArgs& A, int zchunk) {
-  constexpr int NFEAT = MODE == 0 ? 8 : (MODE == 1 ? 6 : 1);
+  constexpr int NFEAT = MODE == 0 ? 8 : ((MODE == 1 || MODE == 3) ? 6 : 1);
   bool all = true, none = true;
   for (int k = 0; k < NFEAT; ++k) { all = all && A.out[k] != nullptr; none = none && A.out[k] == nullptr; }
   if (zchunk > 0) {   // z-marching kernel (everything but ROI-list histograms)
@@ -691,9 +691,10 @@ void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream
     else go(features_march_kernel<MODE, HIST, false, 0>);
     return;
   }
-  if (all && unit) features_kernel<MODE, HIST, true, true><<<grid, block, smem, st>>>(S, A);
-  else if (unit) features_kernel<MODE, HIST, true, false><<<grid, block, smem, st>>>(S, A);
-  else features_kernel<MODE, HIST, false, false><<<grid, block, smem, st>>>(S, A);
+  constexpr int BM = MODE == 3 ? 1 : MODE;   // the raw Hessian only exists in the z-march kernel (checked by the caller)
+  if (all && unit) features_kernel<BM, HIST, true, true><<<grid, block, smem, st>>>(S, A);
+  else if (unit) features_kernel<BM, HIST, true, false><<<grid, block, smem, st>>>(S, A);
+  else features_kernel<BM, HIST, false, false><<<grid, block, smem, st>>>(S, A);
 }
 
 // ROI lists longer than this take the packed-bin path (one block per ROI)
@@ -709,7 +710,7 @@ inline bool march_hist_fits(int nfeat, int n_edges) { return march_hist_smem(nfe
 int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const FeatArgs& A,
                     bool unit_spacing) {
   const bool hist = A.hist.edges != nullptr;
-  const int nfeat = mode == 0 ? 8 : (mode == 1 ? 6 : 1);
+  const int nfeat = mode == 0 ? 8 : ((mode == 1 || mode == 3) ? 6 : 1);
   const int nzo = A.zb1 - A.zb0;
   if (nzo <= 0 || A.nx <= 0 || A.ny <= 0) return IFE_OK;
   dim3 block(kTX, kTY, 1);
@@ -729,6 +730,7 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
     grid.z = (nzo + zchunk - 1) / zchunk;
   }
   if (grid.y > 65535 || grid.z > 65535) return fail(ctx, IFE_E_INVALID, "volume too large for the launch grid");
+  if (mode == 3 && zchunk == 0) return fail(ctx, IFE_E_INVALID, "raw Hessian output needs planes below 2^28 voxels");
   // brick kernel: edge rows as given + uint32 counters; march kernel: rows padded to a power
   // of two + one private 8-bit counter column per thread (falls back to the brick kernel when
   // that does not fit)
@@ -756,6 +758,9 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
   } else if (mode == 1) {
     if (hist) launch_features_t<1, true>(unit_spacing, grid, block, smem, st, S, A, zchunk);
     else launch_features_t<1, false>(unit_spacing, grid, block, 0, st, S, A, zchunk);
+  } else if (mode == 3) {
+    if (hist) return fail(ctx, IFE_E_INVALID, "raw Hessian output has no histogram sink");
+    launch_features_t<3, false>(unit_spacing, grid, block, 0, st, S, A, zchunk);
   } else {
     if (hist) launch_features_t<2, true>(unit_spacing, grid, block, smem, st, S, A, zchunk);
     else launch_features_t<2, false>(unit_spacing, grid, block, 0, st, S, A, zchunk);
@@ -847,6 +852,22 @@ void ife_cuda_destroy(ife_cuda_ctx* ctx) {
 
 const char* ife_cuda_last_error(const ife_cuda_ctx* ctx) {
   return ctx ? ctx->error.c_str() : "null context";
+}
+
+int ife_cuda_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return IFE_E_INVALID;
+  *ptr = nullptr;
+  if (bytes == 0) return IFE_OK;
+  if (cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();   // not sticky: the caller falls back to pageable memory
+    *ptr = nullptr;
+    return IFE_E_CUDA;
+  }
+  return IFE_OK;
+}
+
+void ife_cuda_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
 }
 
 int ife_cuda_set_stream(ife_cuda_ctx* ctx, void* s) {
@@ -1054,6 +1075,34 @@ int ife_cuda_hessian_eigen_features(ife_cuda_ctx* ctx, const float* image, const
   A.nx = dims[0]; A.ny = dims[1]; A.nzb = dims[2]; A.zb0 = 0; A.zb1 = dims[2];
   A.dy_bug = (flags & IFE_FDHF_TOOL_DY_BUG) ? 1 : 0;
   IFE_TRY(launch_features(ctx, 1, make_stencil_coef(spacing), A, is_unit_spacing(spacing)));
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out6, d_out, 6 * n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+int ife_cuda_hessian(ife_cuda_ctx* ctx, const float* image, float* out6, const int dims[3],
+                     const double spacing[3], int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !out6) return fail(ctx, IFE_E_INVALID, "null image pointer");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  const float* d_img;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  float* d_out = out6;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.out[0].reserve(ctx, 6 * n * sizeof(float)));
+    d_out = (float*)ctx->ws.out[0].ptr;
+  }
+  FeatArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.vol = d_img;
+  for (int k = 0; k < 6; ++k) A.out[k] = d_out + (size_t)k * n;
+  A.nx = dims[0]; A.ny = dims[1]; A.nzb = dims[2]; A.zb0 = 0; A.zb1 = dims[2];
+  IFE_TRY(launch_features(ctx, 3, make_stencil_coef(spacing), A, is_unit_spacing(spacing)));
   if (mem == IFE_MEM_HOST) {
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out6, d_out, 6 * n * sizeof(float), cudaMemcpyDeviceToHost,
                                       ctx->stream()));

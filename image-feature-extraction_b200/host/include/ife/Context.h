@@ -2,6 +2,7 @@
 // C-ABI failures (the reference reports failures as itk::ExceptionObject).
 #ifndef IFE_B200_CONTEXT_H
 #define IFE_B200_CONTEXT_H
+#include <ostream>
 #include <stdexcept>
 #include <string>
 
@@ -16,6 +17,8 @@ public:
 private:
   int m_Code;
 };
+
+inline std::ostream& operator<<(std::ostream& os, const ExceptionObject& e) { return os << e.what(); }
 
 class CudaContext {
 public:
@@ -43,4 +46,8 @@ private:
 };
 
 }  // namespace ife
+
+namespace itk {
+using ife::ExceptionObject;
+}
 #endif

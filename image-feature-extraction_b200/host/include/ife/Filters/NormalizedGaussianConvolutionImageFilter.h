@@ -30,10 +30,11 @@ public:
 
   void Update() {
     if (!m_Image || !m_Certainty) throw ExceptionObject(IFE_E_INVALID, "NormalizedGaussianConvolutionImageFilter: inputs not set");
+    m_Image->UpdateSource();
+    m_Certainty->UpdateSource();
     const Geometry& g = m_Image->GetGeometry();
     if (m_Certainty->GetGeometry().size != g.size)
       throw ExceptionObject(IFE_E_INVALID, "NormalizedGaussianConvolutionImageFilter: image and certainty sizes differ");
-    m_Output = ImageType::New();
     m_Output->SetGeometry(g);
     m_Output->Allocate();
     CudaContext& c = CudaContext::Instance();
@@ -44,7 +45,7 @@ public:
   ImageType* GetOutput() { return m_Output.get(); }
 
 private:
-  NormalizedGaussianConvolutionImageFilter() {}
+  NormalizedGaussianConvolutionImageFilter() : m_Output(ImageType::New()) { m_Output->SetSource([this]() { this->Update(); }); }
   const ImageType* m_Image = nullptr;
   const ImageType* m_Certainty = nullptr;
   ScalarRealType m_Sigma = 1.0;
@@ -53,4 +54,8 @@ private:
 };
 
 }  // namespace ife
+
+namespace itk {
+using ife::NormalizedGaussianConvolutionImageFilter;
+}
 #endif

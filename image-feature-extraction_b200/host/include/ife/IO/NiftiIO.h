@@ -41,8 +41,7 @@ inline bool ends_with(const std::string& s, const std::string& e) {
 }
 
 template <typename TOut, typename TIn>
-void convert(const std::vector<unsigned char>& raw, bool swapped, double slope, double inter, std::vector<TOut>& out) {
-  const size_t n = out.size();
+void convert(const std::vector<unsigned char>& raw, bool swapped, double slope, double inter, TOut* out, size_t n) {
   const bool scale = slope != 0.0 && !(slope == 1.0 && inter == 0.0);
   for (size_t i = 0; i < n; ++i) {
     TIn v;
@@ -108,16 +107,16 @@ typename Image<T>::Pointer Read(const std::string& path) {
   }
   gzclose(f);
   if (got != raw.size()) throw std::runtime_error("'" + path + "': truncated voxel data");
-  std::vector<T>& out = img->GetPixelContainer();
+  T* out = img->GetBufferPointer();
   switch (datatype) {
-    case DT_UINT8: convert<T, uint8_t>(raw, swapped, slope, inter, out); break;
-    case DT_INT8: convert<T, int8_t>(raw, swapped, slope, inter, out); break;
-    case DT_INT16: convert<T, int16_t>(raw, swapped, slope, inter, out); break;
-    case DT_UINT16: convert<T, uint16_t>(raw, swapped, slope, inter, out); break;
-    case DT_INT32: convert<T, int32_t>(raw, swapped, slope, inter, out); break;
-    case DT_UINT32: convert<T, uint32_t>(raw, swapped, slope, inter, out); break;
-    case DT_FLOAT32: convert<T, float>(raw, swapped, slope, inter, out); break;
-    case DT_FLOAT64: convert<T, double>(raw, swapped, slope, inter, out); break;
+    case DT_UINT8: convert<T, uint8_t>(raw, swapped, slope, inter, out, n); break;
+    case DT_INT8: convert<T, int8_t>(raw, swapped, slope, inter, out, n); break;
+    case DT_INT16: convert<T, int16_t>(raw, swapped, slope, inter, out, n); break;
+    case DT_UINT16: convert<T, uint16_t>(raw, swapped, slope, inter, out, n); break;
+    case DT_INT32: convert<T, int32_t>(raw, swapped, slope, inter, out, n); break;
+    case DT_UINT32: convert<T, uint32_t>(raw, swapped, slope, inter, out, n); break;
+    case DT_FLOAT32: convert<T, float>(raw, swapped, slope, inter, out, n); break;
+    case DT_FLOAT64: convert<T, double>(raw, swapped, slope, inter, out, n); break;
   }
   return img;
 }

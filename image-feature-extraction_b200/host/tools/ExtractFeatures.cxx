@@ -9,8 +9,12 @@
 #include <string>
 #include <vector>
 
+#include "itkImageFileReader.h"
+#include "itkImageFileWriter.h"
+#include "itkVectorIndexSelectionCastImageFilter.h"
+#include "itkClampImageFilter.h"
+
 #include "ife/Filters/ImageToEmphysemaFeaturesFilter.h"
-#include "ife/IO/NiftiIO.h"
 #include "ife/Util/CmdLine.h"
 
 const std::string VERSION("0.1");
@@ -32,35 +36,65 @@ int main(int argc, char* argv[]) {
     scales.push_back(v);
   }
 
-  typedef ife::Image<float> ImageType;
-  typedef ife::Image<unsigned char> MaskType;
+  // The reference's pipeline (tools/ExtractFeatures.cxx:76-154), spelled with the same itk:: names:
+  // readers -> clamp(0, 1) on the mask -> feature filter -> component selection -> writer, pulled
+  // by writer->Update().  One difference: the scales are handed over together, so the scan is
+  // uploaded once and the download of scale s overlaps the kernels of scale s+1.
+  typedef float PixelType;
+  typedef unsigned char MaskPixelType;
+  const unsigned int Dimension = 3;
+  typedef itk::Image<PixelType, Dimension> ImageType;
+  typedef itk::Image<MaskPixelType, Dimension> MaskType;
+  typedef itk::VectorImage<PixelType, Dimension> VectorImageType;
+
+  typedef itk::ImageFileReader<ImageType> ReaderType;
+  ReaderType::Pointer reader = ReaderType::New();
+  reader->SetFileName(imagePath);
+  typedef itk::ImageFileReader<MaskType> MaskReaderType;
+  MaskReaderType::Pointer maskReader = MaskReaderType::New();
+  maskReader->SetFileName(maskPath);
+
+  typedef itk::ClampImageFilter<MaskType, MaskType> ClampFilterType;
+  ClampFilterType::Pointer clampFilter = ClampFilterType::New();
+  clampFilter->InPlaceOn();
+  clampFilter->SetBounds(0, 1);
+  clampFilter->SetInput(maskReader->GetOutput());
+
+  typedef itk::ImageToEmphysemaFeaturesFilter<ImageType, MaskType, VectorImageType> FeatureFilterType;
+  FeatureFilterType::Pointer featureFilter = FeatureFilterType::New();
+  featureFilter->SetInputImage(reader->GetOutput());
+  featureFilter->SetInputMask(clampFilter->GetOutput());
+  featureFilter->SetSigmas(std::vector<double>(scales.begin(), scales.end()));
+
+  typedef itk::VectorIndexSelectionCastImageFilter<VectorImageType, ImageType> IndexSelectionType;
+  IndexSelectionType::Pointer indexSelectionFilter = IndexSelectionType::New();
+  typedef itk::ImageFileWriter<ImageType> WriterType;
+  WriterType::Pointer writer = WriterType::New();
+  writer->SetInput(indexSelectionFilter->GetOutput());
+
   const std::vector<std::string> featureNames{"GaussianBlur", "GradientMagnitude", "Eigenvalue1", "Eigenvalue2",
                                               "Eigenvalue3", "LaplacianOfGaussian", "GaussianCurvature", "FrobeniusNorm"};
-  std::string outPath;
-  try {
-    ImageType::Pointer image = ife::nifti::Read<float>(imagePath);
-    MaskType::Pointer mask = ife::nifti::Read<unsigned char>(maskPath);
-    for (unsigned char& v : mask->GetPixelContainer()) v = v > 1 ? 1 : v;  // ClampImageFilter(0, 1)
-
-    auto featureFilter = ife::ImageToEmphysemaFeaturesFilter<>::New();
-    featureFilter->SetInputImage(image.get());
-    featureFilter->SetInputMask(mask.get());
-    featureFilter->SetSigmas(std::vector<double>(scales.begin(), scales.end()));
-    featureFilter->UpdateLargestPossibleRegion();
-
-    for (size_t s = 0; s < scales.size(); ++s) {
-      for (unsigned int i = 0; i < featureNames.size(); ++i) {
-        outPath = outBasePath + "_scale_" + std::to_string(scales[s]) + featureNames[i] + OUT_FILE_TYPE;
-        ife::nifti::Write(outPath, image->GetGeometry(), featureFilter->GetOutput(s)->GetComponentPointer(i));
+  for (size_t s = 0; s < scales.size(); ++s) {
+    indexSelectionFilter->SetInput(featureFilter->GetOutput(s));
+    for (unsigned int i = 0; i < featureNames.size(); ++i) {
+      indexSelectionFilter->SetIndex(i);
+      const std::string outPath = outBasePath + "_scale_" + std::to_string(scales[s]) + featureNames[i] + OUT_FILE_TYPE;
+      writer->SetFileName(outPath);
+      try {
+        featureFilter->UpdateLargestPossibleRegion();
+        writer->Update();
+      } catch (itk::ExceptionObject& e) {
+        std::cerr << "Failed to process." << std::endl
+                  << "Image: " << imagePath << std::endl
+                  << "Mask: " << maskPath << std::endl
+                  << "Out: " << outPath << std::endl
+                  << "ExceptionObject: " << e << std::endl;
+        return EXIT_FAILURE;
       }
     }
-  } catch (std::exception& e) {
-    std::cerr << "Failed to process." << std::endl
-              << "Image: " << imagePath << std::endl
-              << "Mask: " << maskPath << std::endl
-              << "Out: " << outPath << std::endl
-              << "ExceptionObject: " << e.what() << std::endl;
-    return EXIT_FAILURE;
   }
+  if (std::getenv("IFE_TIMING"))
+    std::cerr << "[timing] ife_cuda_emphysema_features(IFE_MEM_HOST, page-locked buffers, " << scales.size()
+              << " scales): " << featureFilter->GetLastCallSeconds() << " s" << std::endl;
   return EXIT_SUCCESS;
 }

@@ -45,7 +45,7 @@ int main(int argc, char* argv[]) {
     ife::Image<float>::Pointer image = ife::nifti::Read<float>(imagePath);
     ife::Image<unsigned char>::Pointer mask = ife::nifti::Read<unsigned char>(maskPath);
     if (mask->GetSize() != image->GetSize()) throw std::runtime_error("mask and image dimensions differ");
-    auto hessianFilter = ife::Hessian3DImageFilter<>::New();
+    auto hessianFilter = ife::HessianEigenFeaturesImageFilter<>::New();
     hessianFilter->SetInput(image.get());
     hessianFilter->SetMask(mask.get());
     hessianFilter->SetSigma(sigma);

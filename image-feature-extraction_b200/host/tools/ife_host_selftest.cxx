@@ -65,7 +65,7 @@ int main(int argc, char* argv[]) {
     auto back = ife::nifti::Read<float>(p);
     CHECK(back->GetSize() == img->GetSize());
     CHECK(std::fabs(back->GetSpacing()[2] - 2.5) < 1e-6 && std::fabs(back->GetSpacing()[0] - 0.7) < 1e-6);
-    CHECK(back->GetPixelContainer() == img->GetPixelContainer());
+    CHECK(back->SameBufferContent(*img));
     auto as_u8 = ife::nifti::Read<unsigned char>(p);   // cast on read, like itk::ImageFileReader
     CHECK(as_u8->GetPixel(4, 3, 2) == (unsigned char)(59 * 0.5f - 7));
     std::remove(p.c_str());

@@ -68,6 +68,7 @@ def load_library():
     L.ife_cuda_normalized_gaussian.argtypes = [vp, vp, vp, vp, vp, ip, dp, d, i, i]
     L.ife_cuda_gradient_magnitude.argtypes = [vp, vp, vp, vp, vp, ip, dp, i]
     L.ife_cuda_hessian_eigen_features.argtypes = [vp, vp, vp, vp, ip, dp, d, i, i]
+    L.ife_cuda_hessian.argtypes = [vp, vp, vp, ip, dp, i]
     L.ife_cuda_emphysema_features.argtypes = [vp, vp, vp, vp, ip, dp, dp, i, i]
     L.ife_cuda_emphysema_histograms.argtypes = [vp, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp, i]
     L.ife_cuda_emphysema_histograms_batch.argtypes = [vp, i, vp, vp, ip, dp, dp, i, vp, i, vp, i, vp]
@@ -232,6 +233,13 @@ class Context:
         self._check(self.L.ife_cuda_gradient_magnitude(
             self.h, _ptr(vol), _ptr(mf), _ptr(mu), _ptr(out), _i3(_dims_of(vol)), _d3(spacing),
             MEM_HOST))
+        return out
+
+    def hessian(self, img, spacing=None):
+        """itk::Hessian3DImageFilter: -> (6, nz, ny, nx) planes [Dxx, Dxy, Dxz, Dyy, Dyz, Dzz]."""
+        img = np.ascontiguousarray(img, np.float32)
+        out = np.empty((6,) + img.shape, np.float32)
+        self._check(self.L.ife_cuda_hessian(self.h, _ptr(img), _ptr(out), _i3(_dims_of(img)), _d3(spacing), MEM_HOST))
         return out
 
     def hessian_eigen_features(self, img, mask=None, sigma=0.0, spacing=None, flags=0):

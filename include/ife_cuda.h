@@ -75,6 +75,13 @@ int ife_cuda_abi_version(void);
 int ife_cuda_create(int device, ife_cuda_ctx** ctx);
 void ife_cuda_destroy(ife_cuda_ctx* ctx);
 const char* ife_cuda_last_error(const ife_cuda_ctx* ctx);
+/* Page-locked host memory for the buffers handed to IFE_MEM_HOST calls: the library's
+ * host<->device copies of such a buffer run at full PCIe rate and overlap with the kernels
+ * (a pageable buffer is staged by the driver, synchronously).  No context needed; fails with
+ * IFE_E_CUDA without a device (callers then fall back to malloc).  The C++ facades allocate every
+ * image this way (host/include/ife/Image.h). */
+int ife_cuda_host_alloc(size_t bytes, void** ptr);
+void ife_cuda_host_free(void* ptr);
 /* Use an existing cudaStream_t (e.g. a framework's current stream) instead of the
  * context's own; pass NULL to go back to the context's stream. */
 int ife_cuda_set_stream(ife_cuda_ctx* ctx, void* cuda_stream);
@@ -158,6 +165,15 @@ int ife_cuda_gradient_magnitude(ife_cuda_ctx* ctx, const float* in, const float*
 int ife_cuda_hessian_eigen_features(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
                                     float* out6, const int dims[3], const double spacing[3],
                                     double sigma, int flags, int mem);
+
+/* itk::Hessian3DImageFilter itself (include/ife/Filters/Hessian3DImageFilter.hxx:11-60): the six
+ * central-difference stencils on the image as given (no smoothing, no mask), cross terms as two
+ * chained first-order DerivativeImageFilters (the intermediate is rounded to float), every
+ * stage scaled once by 1/spacing[direction], ZeroFluxNeumann (index-clamped) edges.
+ * out6 = 6 SoA planes in the filter's component order [Dxx, Dxy, Dxz, Dyy, Dyz, Dzz]
+ * (Hessian3DImageFilter.hxx:53-59). */
+int ife_cuda_hessian(ife_cuda_ctx* ctx, const float* image, float* out6, const int dims[3],
+                     const double spacing[3], int mem);
 
 /* itk::ImageToEmphysemaFeaturesFilter for a list of scales
  * (include/ife/Filters/ImageToEmphysemaFeaturesFilter.hxx:94-121, looped over sigma as

@@ -181,6 +181,29 @@ def test_gradient_magnitude_bit_exact(ctx, oracle):
     assert bits_equal(ctx.gradient_magnitude(img, spacing=sp), oracle.gradient_magnitude(img, spacing=sp))
 
 
+def test_hessian_six_components_bit_exact(ctx, oracle):
+    """itk::Hessian3DImageFilter on its own (ife_cuda_hessian): the six stencil outputs
+    [Dxx, Dxy, Dxz, Dyy, Dyz, Dzz] (Hessian3DImageFilter.hxx:53-59) against oracle.hessian6, unit
+    and anisotropic spacing, ragged sizes, the clamped edge planes included."""
+    for shape, sp, seed in (((20, 24, 32), None, 3), ((9, 13, 37), None, 4), ((16, 40, 64), (0.7, 0.8, 2.5), 5),
+                            ((4, 4, 4), None, 6), ((5, 7, 3), (1.0, 2.0, 0.5), 7)):
+        vol = synth.ct_like(shape, seed=seed, n_blobs=5)
+        got = ctx.hessian(vol, spacing=sp)
+        ref = np.moveaxis(oracle.hessian6(vol, spacing=sp), -1, 0)
+        assert got.shape == ref.shape
+        n, worst = mismatch_report(got, ref)
+        assert n == 0, "%s spacing %s: %d Hessian entries differ (max %g)" % (shape, sp, n, worst)
+        # the edge planes are where ZeroFluxNeumann matters: spot-check them explicitly
+        for ax in (1, 2, 3):
+            assert bits_equal(np.take(got, [0, -1], axis=ax), np.take(ref, [0, -1], axis=ax))
+    # the eigen features of ife_cuda_hessian_eigen_features are the functor applied to this output
+    vol = synth.ct_like((12, 16, 32), seed=9, n_blobs=4)
+    H = ctx.hessian(vol)
+    feats = ctx.eigen_features_batch(np.ascontiguousarray(np.moveaxis(H, 0, -1).reshape(-1, 6)))
+    fused = np.moveaxis(ctx.hessian_eigen_features(vol), 0, -1).reshape(-1, 6)
+    assert bits_equal(feats, fused)
+
+
 def test_fd_hessian_features_tool_semantics(ctx, oracle):
     import ife_b200
     shape = (30, 34, 38)
