@@ -67,6 +67,7 @@ struct ife_cuda_ctx {
   uint64_t launches = 0;
   bool use_async = true;   // cp.async software-pipelined Gaussian passes (option "async_passes")
   bool use_tma = true;     // tensor-map staged, field-per-warp Gaussian passes where the layout allows (option "tma_passes")
+  bool use_march4 = true;  // fused feature kernel with four voxels per thread where the layout allows (option "march4")
   bool use_box = true;     // masked paths smooth only the mask's support box (option "support_box")
   int* box_host = nullptr; // pinned: the mask extents come back here once per call
   bool overlap_scales = false;   // option "overlap_scales": features of scale s run beside the passes of scale s+1

@@ -16,6 +16,7 @@
 
 #include "eigen_features.cuh"
 #include "features_march.cuh"
+#include "features_march4.cuh"
 #include "recursive_gaussian.cuh"
 #include "iir_tma.cuh"
 #include "support_box.cuh"
@@ -680,6 +681,18 @@ void launch_features_t(bool unit, dim3 grid, dim3 block, size_t smem, cudaStream
   constexpr int NFEAT = MODE == 0 ? 8 : ((MODE == 1 || MODE == 3) ? 6 : 1);
   bool all = true, none = true;
   for (int k = 0; k < NFEAT; ++k) { all = all && A.out[k] != nullptr; none = none && A.out[k] == nullptr; }
+  if (zchunk < 0) {   // four voxels per thread (features_march4.cuh); grid / block were sized for it
+    zchunk = -zchunk;
+    auto go = [&](void (*kern)(StencilCoef, FeatArgs, int)) {
+      if (smem > 30 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, block, smem, st>>>(S, A, zchunk);
+    };
+    if (HIST && none && unit) go(features_march4_kernel<MODE, HIST, true, HIST ? 2 : 0>);   // histograms only
+    else if (all && unit) go(features_march4_kernel<MODE, HIST, true, 1>);
+    else if (unit) go(features_march4_kernel<MODE, HIST, true, 0>);
+    else go(features_march4_kernel<MODE, HIST, false, 0>);
+    return;
+  }
   if (zchunk > 0) {   // z-marching kernel (everything but ROI-list histograms)
     auto go = [&](void (*kern)(StencilCoef, FeatArgs, int)) {
       if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -750,6 +763,25 @@ int launch_features(ife_cuda_ctx* ctx, int mode, const StencilCoef& S, const Fea
     smem = (size_t)nfeat * (A.hist.n_edges * sizeof(float) + (A.hist.n_edges + 1) * sizeof(uint32_t));
   if (zchunk == 0 && smem > 30 * 1024)
     return fail(ctx, IFE_E_INVALID, "too many histogram edges (%d) for shared memory", A.hist.n_edges);
+  // four voxels per thread when the layout allows 16-byte staging and stores
+  if (zchunk > 0 && ctx->use_march4 && (A.nx & 3) == 0) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    bool ok = al16(A.vol) && (!A.mask_u8 || (reinterpret_cast<uintptr_t>(A.mask_u8) & 3) == 0) &&
+              (!A.hist.packed || al16(A.hist.packed));
+    for (int k = 0; k < nfeat; ++k) ok = ok && al16(A.out[k]);
+    if (ok) {
+      block = dim3(kQX, kQY, 1);
+      grid.x = (A.nx + kQW - 1) / kQW;
+      grid.y = (A.ny + kQY - 1) / kQY;
+      const long long cols = (long long)grid.x * grid.y;
+      const long long want = (8LL * 4 * ctx->sm_count + cols - 1) / cols;   // chunks per column for ~8 waves of blocks
+      int zc = (int)std::max<long long>(16, (nzo + want - 1) / want);
+      zc = std::min(zc, nzo);
+      if (hist) zc = std::min(zc, 63);   // 8-bit private counters: four voxels per plane and thread
+      grid.z = (nzo + zc - 1) / zc;
+      zchunk = -zc;
+    }
+  }
   cudaStream_t st = ctx->stream();
   ProfScope prof(ctx, mode == 2 ? K_OTHER : K_FEATURES);
   if (mode == 0) {
@@ -907,6 +939,7 @@ int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return IFE_E_INVALID;
   if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
   if (std::strcmp(name, "tma_passes") == 0) { ctx->use_tma = value != 0; return IFE_OK; }
+  if (std::strcmp(name, "march4") == 0) { ctx->use_march4 = value != 0; return IFE_OK; }
   if (std::strcmp(name, "support_box") == 0) { ctx->use_box = value != 0; return IFE_OK; }
   if (std::strcmp(name, "overlap_scales") == 0) { ctx->overlap_scales = value != 0; return IFE_OK; }
   return fail(ctx, IFE_E_INVALID, "unknown option '%s'", name);

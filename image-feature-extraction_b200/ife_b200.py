@@ -146,6 +146,10 @@ class Context:
                                "(there is no CPU fallback)" % device)
         self.h = h
         self.set_arith(arith)
+        # A/B switches for the profiling scripts: IFE_CUDA_OPTIONS="march4=0,tma_passes=0"
+        for kv in filter(None, os.environ.get("IFE_CUDA_OPTIONS", "").split(",")):
+            name, _, val = kv.partition("=")
+            self.set_option(name.strip(), int(val or 1))
 
     def close(self):
         if getattr(self, "h", None):
