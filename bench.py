@@ -56,7 +56,7 @@ ALGO_BYTES_HIST = {"gauss_pass_z": 13, "gauss_pass_x": 16, "gauss_pass_y": 12, "
 # what limits each kernel according to the ncu captures under profiles/ (HBM is < 60 % busy in
 # all of them): the passes by FP64-pipe issue + dependent-chain latency, the fused kernel by
 # instruction issue
-BOUND_NCU = {"gauss_pass_z": "fp64", "gauss_pass_x": "fp64", "gauss_pass_y": "fp64", "features_fused": "issue"}
+BOUND_NCU = {"gauss_pass_z": "issue+fp64", "gauss_pass_x": "hbm+fp64", "gauss_pass_y": "issue+fp64", "features_fused": "issue"}
 CPU_SAMPLE_NZ = 64                   # CPU arms (cpu_baseline, --impl reference): 512 x 512 x 64, all four scales
 CPU_SAMPLE = "%dx%dx%d sub-volume x %d scales" % (DIMS[0], DIMS[1], CPU_SAMPLE_NZ, len(SIGMAS))
 HIST_SAMPLE_Z0 = 32                  # hist parity sample: planes [32, 96) -- the lung mask starts at z = 50
@@ -470,6 +470,20 @@ def leg_extract(env, img, mask):
                 "pipeline": {"algo_bytes_per_voxel_scale": pipe_b,
                              "achieved_gbs": pipe_b * units / (ms_per_step * 1e-3) / 1e9,
                              "frac": pipe_b * units / (ms_per_step * 1e-3) / 1e9 / env.peak}}
+    # the other arithmetic mode of the recursion (the reference built without / with FMA contraction:
+    # a stock x86-64 build is PLAIN), a short device-resident measurement for the record
+    other = None
+    if env.world == 1:
+        alt = env.ife.ARITH_PLAIN if args.arith == "fma" else env.ife.ARITH_FMA
+        ctx.set_arith(alt)
+        try:
+            ms_o, _, _, _ = env.timed(step, max(3, min(args.steps, 5)), 2, clocks=False)
+        finally:
+            ctx.set_arith(env.ife.ARITH_FMA if args.arith == "fma" else env.ife.ARITH_PLAIN)
+        n_o = max(3, min(args.steps, 5))
+        other = {"arith": "plain" if args.arith == "fma" else "fma", "ms_per_step": ms_o / n_o,
+                 "value": units / (ms_o / n_o * 1e-3) / 1e9, "unit": "Gvoxel/s",
+                 "note": "same workload, device-resident, the recursion's other arithmetic mode (bit-exact against the oracle in that mode)"}
     e2e = None
     if not args.no_e2e:
         h_img = torch.empty((nz, ny, nx), dtype=torch.float32, pin_memory=True).copy_(img)
@@ -501,7 +515,7 @@ def leg_extract(env, img, mask):
         del out
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "e2e": e2e,
-            "launches": launches, "clocks": clocks}
+            "launches": launches, "clocks": clocks, "other_arith": other}
 
 
 # ------------------------------------------------------------------------------------------
@@ -847,7 +861,7 @@ def _main(out_stream):
                             "parallelism": "1 scan per GPU, no data-path collective",
                             "l2": "inputs (525 MB/scan) and every intermediate are larger than the 126 MB L2; no flush needed"},
                     roofline=x["roofline"], e2e=x["e2e"], cpu_baseline=cpu, parity=parity,
-                    gpu_launches=x["launches"], clocks=x["clocks"])
+                    gpu_launches=x["launches"], clocks=x["clocks"], other_arith=x["other_arith"])
         if not args.no_hist:
             line["hist"] = leg_hist(env, "lung", args.rois)
         if not args.no_slab:

@@ -12,13 +12,13 @@
 #include <vector>
 
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include "eigen_features.cuh"
 #include "features_march.cuh"
 #include "features_march4.cuh"
 #include "recursive_gaussian.cuh"
 #include "iir_tma.cuh"
+#include "radix_sort.cuh"
 #include "support_box.cuh"
 #include "ife_ctx.h"
 
@@ -1506,6 +1506,30 @@ int ife_cuda_intensity_roi_histograms(ife_cuda_ctx* ctx, const float* image, con
   return IFE_OK;
 }
 
+// In-place device sort of n floats at d_data (csrc/radix_sort.cuh): 8 passes of count / scan / scatter
+// between d_data and a scratch buffer; after an even number of passes the result is back in d_data.
+static int radix_sort_device(ife_cuda_ctx* ctx, float* d_data, size_t n) {
+  const unsigned n_tiles = (unsigned)((n + kRsTile - 1) / kRsTile);
+  IFE_TRY(ctx->ws.out[1].reserve(ctx, n * sizeof(uint32_t)));
+  IFE_TRY(ctx->ws.counts.reserve(ctx, (size_t)kRsBins * n_tiles * sizeof(uint32_t)));
+  uint32_t* a = reinterpret_cast<uint32_t*>(d_data);
+  uint32_t* b = (uint32_t*)ctx->ws.out[1].ptr;
+  uint32_t* cnt = (uint32_t*)ctx->ws.counts.ptr;
+  cudaStream_t st = ctx->stream();
+  const unsigned g = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+  rs_to_keys_kernel<<<g, 256, 0, st>>>(a, n);
+  for (int pass = 0; pass < 8; ++pass) {
+    rs_count_kernel<<<n_tiles, kRsThreads, 0, st>>>(a, n, 4 * pass, cnt, n_tiles);
+    rs_scan_kernel<<<1, 1024, 0, st>>>(cnt, (size_t)kRsBins * n_tiles);
+    rs_scatter_kernel<<<n_tiles, kRsThreads, 0, st>>>(a, b, n, 4 * pass, cnt, n_tiles);
+    std::swap(a, b);
+  }
+  rs_from_keys_kernel<<<g, 256, 0, st>>>(a, n);   // a == d_data again
+  ctx->launches += 26;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
 int ife_cuda_sort_f32(ife_cuda_ctx* ctx, float* data, size_t n, int mem) {
   if (!ctx) return IFE_E_INVALID;
   if (n == 0) return IFE_OK;
@@ -1515,18 +1539,115 @@ int ife_cuda_sort_f32(ife_cuda_ctx* ctx, float* data, size_t n, int mem) {
   const float* d_in_c;
   IFE_TRY(stage_in(ctx, ctx->ws.in_img, (const float*)data, n, mem, &d_in_c));
   float* d_in = const_cast<float*>(d_in_c);
-  IFE_TRY(ctx->ws.out[0].reserve(ctx, n * sizeof(float)));
-  float* d_alt = (float*)ctx->ws.out[0].ptr;
-  cub::DoubleBuffer<float> keys(d_in, d_alt);
-  size_t tmp_bytes = 0;
-  IFE_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (int)n, 0, 32, ctx->stream()));
-  IFE_TRY(ctx->ws.blur.reserve(ctx, tmp_bytes));
-  IFE_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(ctx->ws.blur.ptr, tmp_bytes, keys, (int)n, 0, 32, ctx->stream()));
-  ctx->launches++;
-  const cudaMemcpyKind kind = mem == IFE_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  if (mem == IFE_MEM_HOST || keys.Current() != data)
-    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(data, keys.Current(), n * sizeof(float), kind, ctx->stream()));
-  if (mem == IFE_MEM_HOST) IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  IFE_TRY(radix_sort_device(ctx, d_in, n));
+  if (mem == IFE_MEM_HOST) {
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(data, d_in, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream()));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream()));
+  }
+  return IFE_OK;
+}
+
+// The compaction sink of the bin-edge determination: features on the device, only the sampled
+// voxels' values leave it.
+int ife_cuda_emphysema_feature_samples(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                       const uint8_t* select, const long long* index, size_t n_index,
+                                       const int dims[3], const double spacing[3], const double* sigmas,
+                                       int n_sigma, int sorted, float* out, size_t* n_out, int mem) {
+  if (!ctx) return IFE_E_INVALID;
+  if (!image || !mask || !sigmas || n_sigma <= 0 || !n_out) return fail(ctx, IFE_E_INVALID, "null pointer argument");
+  if ((select != nullptr) == (index != nullptr)) return fail(ctx, IFE_E_INVALID, "give either a selection mask or an index list");
+  IFE_TRY(check_dims(ctx, dims, spacing));
+  IFE_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int nx = dims[0], ny = dims[1], nz = dims[2];
+  const size_t n = (size_t)nx * ny * nz;
+  cudaStream_t st = ctx->stream();
+  const float* d_img;
+  const uint8_t* d_mask;
+  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
+  // which voxels: selection flags -> per-tile counts -> offsets (host prefix over a few thousand
+  // integers); or an explicit index list
+  const unsigned n_tiles = (unsigned)((n + kCsTile - 1) / kCsTile);
+  const uint8_t* d_sel = nullptr;
+  const long long* d_idx = nullptr;
+  size_t n_sel = n_index;
+  if (select) {
+    if (mem == IFE_MEM_HOST) {
+      IFE_TRY(ctx->ws.slab_mask.reserve(ctx, n));
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.slab_mask.ptr, select, n, cudaMemcpyHostToDevice, st));
+      d_sel = (const uint8_t*)ctx->ws.slab_mask.ptr;
+    } else {
+      d_sel = select;
+    }
+    IFE_TRY(ctx->ws.counts.reserve(ctx, (size_t)n_tiles * sizeof(uint32_t)));
+    IFE_TRY(ctx->ws.rois.reserve(ctx, (size_t)n_tiles * sizeof(uint64_t)));
+    cs_count_kernel<<<n_tiles, kCsThreads, 0, st>>>(d_sel, n, (uint32_t*)ctx->ws.counts.ptr);
+    ctx->launches++;
+    std::vector<uint32_t> cnt(n_tiles);
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(cnt.data(), ctx->ws.counts.ptr, (size_t)n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    std::vector<uint64_t> off(n_tiles);
+    uint64_t run = 0;
+    for (unsigned t = 0; t < n_tiles; ++t) { off[t] = run; run += cnt[t]; }
+    n_sel = (size_t)run;
+    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.rois.ptr, off.data(), (size_t)n_tiles * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // `off` leaves scope
+  } else {
+    for (size_t j = 0; j < n_index && mem == IFE_MEM_HOST; ++j)
+      if (index[j] < 0 || (size_t)index[j] >= n) return fail(ctx, IFE_E_INVALID, "sample index %zu out of range", j);
+    if (mem == IFE_MEM_HOST) {
+      IFE_TRY(ctx->ws.rois.reserve(ctx, std::max<size_t>(n_index, 1) * sizeof(long long)));
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.rois.ptr, index, n_index * sizeof(long long), cudaMemcpyHostToDevice, st));
+      d_idx = (const long long*)ctx->ws.rois.ptr;
+    } else {
+      d_idx = index;
+    }
+  }
+  *n_out = n_sel;
+  if (n_sel == 0 || !out) return IFE_OK;   // out == null: the caller only asked how many
+  if (n_sel > (size_t)0x7fffffff) return fail(ctx, IFE_E_INVALID, "too many samples (%zu)", n_sel);
+
+  IFE_TRY(reserve_smoothing(ctx, 2, nx, ny, nz));
+  IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
+  IFE_TRY(ctx->ws.out[0].reserve(ctx, 8 * n * sizeof(float)));
+  int box[6];
+  bool have_box;
+  IFE_TRY(compute_support_box(ctx, d_mask, nx, ny, nz, nullptr, 0, box, &have_box));
+  MaskedPlan plan;
+  IFE_TRY(plan_masked(ctx, have_box, 0, d_img, d_mask, nx, ny, nz, nullptr, 0, &plan));
+  const size_t rows_bytes = (size_t)8 * n_sel * sizeof(float);
+  float* d_rows = out;
+  if (mem == IFE_MEM_HOST) {
+    IFE_TRY(ctx->ws.packed.reserve(ctx, rows_bytes));
+    d_rows = (float*)ctx->ws.packed.ptr;
+  }
+  float* blur = (float*)ctx->ws.blur.ptr;
+  float* feats = (float*)ctx->ws.out[0].ptr;
+  const StencilCoef S = make_stencil_coef(spacing);
+  for (int s = 0; s < n_sigma; ++s) {
+    IFE_TRY(smooth_masked(ctx, plan, d_img, d_mask, blur, nx, ny, nz, spacing, sigmas[s]));
+    FeatArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.vol = blur; A.mask_u8 = d_mask;
+    for (int k = 0; k < 8; ++k) A.out[k] = feats + (size_t)k * n;
+    A.nx = nx; A.ny = ny; A.nzb = nz; A.zb0 = 0; A.zb1 = nz;
+    IFE_TRY(launch_features(ctx, 0, S, A, is_unit_spacing(spacing)));
+    float* rows = mem == IFE_MEM_HOST ? d_rows : out + (size_t)s * 8 * n_sel;
+    if (d_sel) {
+      cs_gather_kernel<<<n_tiles, kCsThreads, 0, st>>>(d_sel, n, (const uint64_t*)ctx->ws.rois.ptr, feats, n, 8, rows, n_sel);
+    } else {
+      const unsigned g = (unsigned)std::min<size_t>((n_sel + 255) / 256, (size_t)ctx->sm_count * 16);
+      cs_gather_index_kernel<<<g, 256, 0, st>>>(d_idx, n_sel, feats, n, 8, rows, n_sel);
+    }
+    ctx->launches++;
+    IFE_CUDA_TRY(ctx, cudaGetLastError());
+    if (sorted)
+      for (int k = 0; k < 8; ++k) IFE_TRY(radix_sort_device(ctx, rows + (size_t)k * n_sel, n_sel));
+    if (mem == IFE_MEM_HOST) {
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)s * 8 * n_sel, rows, rows_bytes, cudaMemcpyDeviceToHost, st));
+      IFE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+  }
   return IFE_OK;
 }
 

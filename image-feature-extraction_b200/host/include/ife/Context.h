@@ -2,6 +2,7 @@
 // C-ABI failures (the reference reports failures as itk::ExceptionObject).
 #ifndef IFE_B200_CONTEXT_H
 #define IFE_B200_CONTEXT_H
+#include <cstdlib>
 #include <ostream>
 #include <stdexcept>
 #include <string>
@@ -31,6 +32,15 @@ public:
       const int rc = ife_cuda_create(m_Device, &m_Ctx);
       if (rc != IFE_OK)
         throw ExceptionObject(rc, "ife_cuda_create failed: no usable CUDA device (this library has no CPU fallback)");
+      // IFE_ARITH=plain|fma selects which build of the reference the recursive Gaussian reproduces bit
+      // for bit: "plain" = every multiply and add rounded (a stock x86-64 build of ITK, no -mfma),
+      // "fma" = the contraction of a -mfma build (the library default, ~15 % faster)
+      if (const char* a = std::getenv("IFE_ARITH")) {
+        const std::string v(a);
+        if (v == "plain") ife_cuda_set_arith(m_Ctx, IFE_ARITH_PLAIN);
+        else if (v == "fma") ife_cuda_set_arith(m_Ctx, IFE_ARITH_FMA);
+        else throw ExceptionObject(IFE_E_INVALID, "IFE_ARITH must be 'plain' or 'fma'");
+      }
     }
     return m_Ctx;
   }

@@ -7,7 +7,8 @@
 // (-S 0) or at -S random such voxels per scale (:171-264); per (scale, feature) the samples
 // are sorted and equal-frequency edges determined (:282-296); the output is the
 // histogram-spec file MakeBag reads (two '#' header lines, one row of bins-1 edges each).
-// Features come from the GPU (all scales in one call), the sort is a device radix sort.
+// Features are computed on the GPU and only the sampled values leave it (compaction sink); the
+// sort is the library's own device radix sort.
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -16,7 +17,6 @@
 #include <vector>
 
 #include "ife/Context.h"
-#include "ife/Filters/ImageToEmphysemaFeaturesFilter.h"
 #include "ife/IO/NiftiIO.h"
 #include "ife/Statistics/DetermineEdgesForEqualizedHistogram.h"
 #include "ife/Util/CmdLine.h"
@@ -86,29 +86,40 @@ int main(int argc, char* argv[]) {
         for (unsigned a : foreground) if (v == a) { fg[i] = 1; break; }
         nFg += fg[i];
       }
-      auto filter = ife::ImageToEmphysemaFeaturesFilter<>::New();
-      filter->SetInputImage(image.get());
-      filter->SetInputMask(mask.get());
-      filter->SetSigmas(std::vector<double>(scales.begin(), scales.end()));
-      filter->Update();
-      for (size_t s = 0; s < scales.size(); ++s) {
-        const auto* out = filter->GetOutput(s);
-        if (nSamples == 0) {
-          for (size_t j = 0; j < numFeatures; ++j) {
-            const float* plane = out->GetComponentPointer((unsigned)j);
-            std::vector<float>& dst = samples[j + s * numFeatures];
-            dst.reserve(dst.size() + nFg);
-            for (size_t i = 0; i < n; ++i) if (fg[i]) dst.push_back(plane[i]);
-          }
-        } else {
-          if (nFg == 0) throw std::runtime_error("mask has no foreground voxel to sample");
-          std::uniform_int_distribution<size_t> pick(0, n - 1);
-          for (unsigned got = 0; got < nSamples;) {
+      // The features stay on the device; only the sampled voxels' values come back ("compaction
+      // sink", ife_cuda_emphysema_feature_samples): all foreground voxels in voxel order (-S 0), or
+      // -S random foreground voxels per scale, drawn here exactly as the reference draws them.
+      ife::CudaContext& c = ife::CudaContext::Instance();
+      const ife::Geometry& g = image->GetGeometry();
+      std::vector<double> sig(scales.begin(), scales.end());
+      if (nSamples == 0) {
+        if (nFg) {
+          std::vector<float> rows(scales.size() * numFeatures * nFg);
+          size_t got = 0;
+          c.Check(ife_cuda_emphysema_feature_samples(c.Handle(), image->GetBufferPointer(), mask->GetBufferPointer(),
+                                                     fg.data(), nullptr, 0, g.size.data(), g.spacing.data(), sig.data(),
+                                                     (int)sig.size(), 0, rows.data(), &got, IFE_MEM_HOST));
+          if (got != nFg) throw std::runtime_error("sample count mismatch");
+          for (size_t r = 0; r < scales.size() * numFeatures; ++r)
+            samples[r].insert(samples[r].end(), rows.begin() + r * nFg, rows.begin() + (r + 1) * nFg);
+        }
+      } else {
+        if (nFg == 0) throw std::runtime_error("mask has no foreground voxel to sample");
+        std::uniform_int_distribution<size_t> pick(0, n - 1);
+        for (size_t s = 0; s < scales.size(); ++s) {
+          std::vector<long long> index;
+          index.reserve(nSamples);
+          while (index.size() < nSamples) {
             const size_t i = pick(gen);
-            if (!fg[i]) continue;
-            for (size_t j = 0; j < numFeatures; ++j) samples[j + s * numFeatures].push_back(out->GetComponentPointer((unsigned)j)[i]);
-            ++got;
+            if (fg[i]) index.push_back((long long)i);
           }
+          std::vector<float> rows(numFeatures * index.size());
+          size_t got = 0;
+          c.Check(ife_cuda_emphysema_feature_samples(c.Handle(), image->GetBufferPointer(), mask->GetBufferPointer(),
+                                                     nullptr, index.data(), index.size(), g.size.data(), g.spacing.data(),
+                                                     &sig[s], 1, 0, rows.data(), &got, IFE_MEM_HOST));
+          for (size_t j = 0; j < numFeatures; ++j)
+            samples[j + s * numFeatures].insert(samples[j + s * numFeatures].end(), rows.begin() + j * got, rows.begin() + (j + 1) * got);
         }
       }
     } catch (std::exception& e) {

@@ -76,6 +76,10 @@ def load_library():
     L.ife_cuda_intensity_roi_histograms.argtypes = [vp, vp, vp, ip, vp, i, vp, i, vp, i]
     L.ife_cuda_eigen_features_batch.argtypes = [vp, vp, vp, sz, i]
     L.ife_cuda_sort_f32.argtypes = [vp, vp, sz, i]
+    L.ife_cuda_emphysema_feature_samples.argtypes = [vp, vp, vp, vp, vp, sz, ip, dp, dp, i, i, vp, C.POINTER(sz), i]
+    L.ife_cuda_host_alloc.argtypes = [sz, C.POINTER(C.c_void_p)]
+    L.ife_cuda_host_free.argtypes = [vp]
+    L.ife_cuda_host_free.restype = None
     L.ife_cuda_comm_unique_id.argtypes = [vp, vp]
     L.ife_cuda_comm_init.argtypes = [vp, vp, i, i]
     L.ife_cuda_comm_destroy.argtypes = [vp]
@@ -323,6 +327,24 @@ class Context:
         v = np.array(values, np.float32).ravel()
         self._check(self.L.ife_cuda_sort_f32(self.h, _ptr(v) if v.size else None, v.size, MEM_HOST))
         return v
+
+    def feature_samples(self, img, mask, sigmas, select=None, index=None, sort=False, spacing=None):
+        """The 8 features at the selected voxels only: -> (n_sigma, 8, n_selected) rows, in voxel
+        order (select: uint8 flags) or list order (index: voxel indices), optionally sorted."""
+        img = np.ascontiguousarray(img, np.float32)
+        m = np.ascontiguousarray(mask, np.uint8)
+        sigmas = list(sigmas)
+        sel = None if select is None else np.ascontiguousarray(select, np.uint8)
+        idx = None if index is None else np.ascontiguousarray(index, np.int64)
+        n_idx = 0 if idx is None else idx.size
+        n_out = C.c_size_t(0)
+        args = (self.h, _ptr(img), _ptr(m), _ptr(sel), _ptr(idx), n_idx, _i3(_dims_of(img)), _d3(spacing),
+                _dn(sigmas), len(sigmas), 1 if sort else 0)
+        self._check(self.L.ife_cuda_emphysema_feature_samples(*args, None, C.byref(n_out), MEM_HOST))
+        out = np.empty((len(sigmas), 8, n_out.value), np.float32)
+        if n_out.value:
+            self._check(self.L.ife_cuda_emphysema_feature_samples(*args, _ptr(out), C.byref(n_out), MEM_HOST))
+        return out
 
     def eigen_features_batch(self, A6):
         A6 = np.ascontiguousarray(A6, np.float32).reshape(-1, 6)

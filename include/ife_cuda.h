@@ -235,10 +235,26 @@ int ife_cuda_intensity_roi_histograms(ife_cuda_ctx* ctx, const float* image, con
                                       const int* rois, int n_roi, uint32_t* counts, int mem);
 
 /* Ascending in-place sort of n floats: the `std::sort` of the feature samples in
- * tools/DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx:282-283 (device radix
- * sort; the equal-frequency edge walk of DetermineEdgesForEqualizedHistogram.h then runs
- * on the host, it touches O(bins * log n) samples). */
+ * tools/DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx:282-283.  A radix sort of
+ * this library's own (csrc/radix_sort.cuh: 4-bit digits, count / scan / stable scatter; no
+ * CUB); the equal-frequency edge walk of DetermineEdgesForEqualizedHistogram.h then runs on
+ * the host, it touches O(bins * log n) samples. */
 int ife_cuda_sort_f32(ife_cuda_ctx* ctx, float* data, size_t n, int mem);
+
+/* The sampling loop of tools/DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx:171-264
+ * with the feature volumes never leaving the device ("compaction sink"): for every scale the 8
+ * features of ImageToEmphysemaFeaturesFilter are computed on the device and only the sampled
+ * voxels' values are kept, as dense rows out[s][k][j], j < *n_out.
+ *   select != NULL: uint8 flags per voxel; the selected voxels in voxel-index order (the "all
+ *                   foreground voxels" mode, -S 0); index must be NULL;
+ *   index  != NULL: n_index voxel indices (x + nx*(y + ny*z)), repeats allowed, order kept (the
+ *                   random sampling mode); select must be NULL.
+ * sorted != 0 additionally sorts every row ascending on the device (ife_cuda_sort_f32's kernels),
+ * which is what the edge walk wants.  out == NULL only counts (*n_out). */
+int ife_cuda_emphysema_feature_samples(ife_cuda_ctx* ctx, const float* image, const uint8_t* mask,
+                                       const uint8_t* select, const long long* index, size_t n_index,
+                                       const int dims[3], const double spacing[3], const double* sigmas,
+                                       int n_sigma, int sorted, float* out, size_t* n_out, int mem);
 
 /* EigenvalueFeaturesFunctor<float> (and through it Symmetric3x3EigenvalueSolver<float>,
  * include/ife/Numerics/Symmetric3x3EigenvalueSolver.h:33-132) over n interleaved

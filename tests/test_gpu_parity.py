@@ -488,6 +488,39 @@ def test_histograms_batch_equals_one_call_per_scan(ctx):
     assert np.array_equal(ctx.emphysema_histograms_batch(imgs, [mask] * 3, sigmas, edges, rois), one)
 
 
+def test_radix_sort_and_compaction_sink(ctx):
+    """The step before binning (DetermineHistogramBinEdges_MultiScaleEigenvalueFeatures.cxx:171-296):
+    the library's own radix sort against numpy (ties, negatives, zeros of both signs, infinities,
+    sizes around the tile boundaries) and the compaction sink -- the features at the selected
+    voxels only -- against the full feature volumes."""
+    rng = np.random.default_rng(17)
+    for n in (1, 2, 255, 2048, 2049, 4097, 100_003, 1_500_000):
+        v = rng.normal(0, 50, n).astype(np.float32)
+        v[rng.integers(0, n, max(1, n // 7))] = np.float32(3.25)          # ties
+        v[rng.integers(0, n, max(1, n // 50))] = np.float32(0.0)
+        v[rng.integers(0, n, max(1, n // 60))] = np.float32(-0.0)
+        if n > 100:
+            v[:3] = [np.inf, -np.inf, np.float32(1e-42)]                   # infinities, a denormal
+        got = ctx.sort(v.copy())
+        ref = np.sort(v)
+        assert np.array_equal(got, ref), "n=%d" % n                        # -0.0 == 0.0 under array_equal, as under std::sort
+    shape = (24, 40, 64)
+    img = synth.ct_like(shape, seed=61, n_blobs=8)
+    mask = synth.clamp01(synth.lung_mask(shape))
+    sigmas = [0.6, 2.4]
+    full = ctx.emphysema_features(img, mask, sigmas)
+    fg = (mask != 0) & (rng.uniform(0, 1, shape) < 0.6)                   # a subset of the foreground
+    rows = ctx.feature_samples(img, mask, sigmas, select=fg.astype(np.uint8))
+    assert rows.shape == (2, 8, int(fg.sum()))
+    assert bits_equal(rows, full[:, :, fg])                               # voxel order = C order of the flags
+    srt = ctx.feature_samples(img, mask, sigmas, select=fg.astype(np.uint8), sort=True)
+    assert bits_equal(srt, np.sort(full[:, :, fg], axis=2))
+    idx = rng.integers(0, img.size, 5000)                                  # random sampling with repeats
+    rows = ctx.feature_samples(img, mask, sigmas, index=idx)
+    assert bits_equal(rows, full.reshape(2, 8, -1)[:, :, idx])
+    assert ctx.feature_samples(img, mask, sigmas, select=np.zeros(shape, np.uint8)).shape == (2, 8, 0)
+
+
 def test_bad_arguments_are_rejected(ctx):
     import ctypes
     import ife_b200
