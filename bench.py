@@ -344,6 +344,27 @@ class QuietStdout:
         return False
 
 
+def bind_to_gpu_numa_node(index):
+    """CPU affinity of this process := the CPUs NVML reports as local to GPU `index`.
+    Returns a short description for the JSON line (or why nothing was done)."""
+    if os.environ.get("IFE_BENCH_NO_BIND"):
+        return "off (IFE_BENCH_NO_BIND)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return "NUMA-local to GPU %d: %d CPUs" % (phys, len(cpus))
+    except Exception as e:      # no NVML, restricted container: stay where we are
+        return "unchanged (%s)" % type(e).__name__
+
+
 class Env:
     """Everything a leg needs: torch, the process group, the context and its stream."""
 
@@ -360,6 +381,9 @@ class Env:
                              "(use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        # run on the CPUs next to this GPU's PCIe root, so that the page-locked host buffers of the
+        # e2e legs are first-touched on the local NUMA node (every rank otherwise lands on node 0)
+        self.affinity = bind_to_gpu_numa_node(self.local_rank)
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
@@ -859,6 +883,7 @@ def _main(out_stream):
         line = dict(base, value=x["value"], ms_per_step=x["ms_per_step"],
                     config={"workload": WORKLOAD, "mask": args.mask, "arith": args.arith,
                             "parallelism": "1 scan per GPU, no data-path collective",
+                            "cpu_affinity": env.affinity,
                             "l2": "inputs (525 MB/scan) and every intermediate are larger than the 126 MB L2; no flush needed"},
                     roofline=x["roofline"], e2e=x["e2e"], cpu_baseline=cpu, parity=parity,
                     gpu_launches=x["launches"], clocks=x["clocks"], other_arith=x["other_arith"])

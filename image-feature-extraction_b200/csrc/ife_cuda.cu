@@ -232,7 +232,7 @@ int make_map3(ife_cuda_ctx* ctx, CUtensorMap* m, const void* base, bool u8, long
 #define IFE_TMA_MINB_Z 11    // z pass: 20.2 KB of shared memory per block (two roles + the tile of ones)
 #endif
 #ifndef IFE_TMA_MINB_X
-#define IFE_TMA_MINB_X 9
+#define IFE_TMA_MINB_X 8
 #endif
 
 template <int AXIS, int INMODE, bool DIVIDE>

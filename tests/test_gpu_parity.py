@@ -521,6 +521,29 @@ def test_radix_sort_and_compaction_sink(ctx):
     assert ctx.feature_samples(img, mask, sigmas, select=np.zeros(shape, np.uint8)).shape == (2, 8, 0)
 
 
+def test_workspace_growth_between_host_calls(oracle):
+    """The grow-only workspace is reallocated while copies of the previous call may still be in
+    flight on the context's copy stream (IFE_MEM_HOST multi-scale calls download scale s while scale
+    s+1 computes): a small multi-scale call followed at once by larger ones, on a FRESH context, must
+    give each call its own correct result."""
+    import ife_b200
+    c = ife_b200.Context(0)
+    try:
+        sig = [0.6, 1.2, 2.4]
+        outs, refs = [], []
+        for shape, seed in (((12, 16, 32), 1), ((24, 40, 64), 2), ((20, 24, 48), 3), ((40, 64, 96), 4)):
+            img = synth.ct_like(shape, seed=70 + seed, n_blobs=5)
+            mask = synth.clamp01(synth.lung_mask(shape))
+            outs.append(c.emphysema_features(img, mask, sig))          # host pointers, no sync in between but the call's own
+            refs.append((img, mask))
+        for out, (img, mask) in zip(outs, refs):
+            ref = np.stack([oracle.emphysema_features(img, mask, s, arith=1) for s in sig])
+            assert mismatch_report(out[:, :2], ref[:, :2])[0] == 0
+            assert_eigen_parity(np.moveaxis(out[:, 2:], 1, -1), np.moveaxis(ref[:, 2:], 1, -1), "growth")
+    finally:
+        c.close()
+
+
 def test_bad_arguments_are_rejected(ctx):
     import ctypes
     import ife_b200
