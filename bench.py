@@ -665,8 +665,25 @@ def leg_hist(env, mask_kind="lung", n_rois=50, headline=False):
         dtb = env.max_over_ranks((time.perf_counter() - t0) / nb)
         e2e["batch"] = {"value": env.world * units / dtb / 1e9, "unit": "Gvoxel/s", "ms_per_scan": dtb * 1e3,
                         "scans_per_call": nb, "api": "ife_cuda_emphysema_histograms_batch (host scans, uploads overlapped)"}
+        # the same batch with the scans as int16 on the host (CT's type on disk; option
+        # "host_image_i16": 2 bytes per voxel up, widened on the device) -- the synthetic scan is
+        # rounded to integers for this sub-leg, so its histograms are those of the rounded scan
+        h_i16 = torch.empty((nz, ny, nx), dtype=torch.int16, pin_memory=True).copy_(img.round().to(torch.int16))
+        ctx.set_option("host_image_i16", 1)
+        try:
+            imgs16 = [h_i16.numpy()] * nb
+            ctx.emphysema_histograms_batch(imgs16, masks, SIGMAS, edges, None, _raw_image=True)
+            env.barrier()
+            t0 = time.perf_counter()
+            ctx.emphysema_histograms_batch(imgs16, masks, SIGMAS, edges, None, _raw_image=True)
+            dt16 = env.max_over_ranks((time.perf_counter() - t0) / nb)
+        finally:
+            ctx.set_option("host_image_i16", 0)
+        e2e["batch_int16_upload"] = {"value": env.world * units / dt16 / 1e9, "unit": "Gvoxel/s", "ms_per_scan": dt16 * 1e3,
+                                     "scans_per_call": nb, "h2d_bytes_per_scan": int(h_i16.numel() * 2 + h_mask.numel()),
+                                     "api": "ife_cuda_emphysema_histograms_batch, option host_image_i16"}
         res["e2e"] = e2e
-        del h_img, h_mask
+        del h_img, h_mask, h_i16
     del img, mask, counts, counts_r
     torch.cuda.empty_cache()
     if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:

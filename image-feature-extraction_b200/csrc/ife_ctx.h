@@ -24,6 +24,7 @@ struct Workspace {
   DeviceBuffer blur, blur2;     // smoothed volume fed to the fused feature kernel (blur2: option overlap_scales)
   DeviceBuffer ckpt;            // recursion checkpoints (double)
   DeviceBuffer in_img, in_mask; // staging for IFE_MEM_HOST inputs
+  DeviceBuffer in_i16;          // int16 images on their way to float (option "host_image_i16"; two slots)
   DeviceBuffer out[2];          // staging for IFE_MEM_HOST outputs (double-buffered per scale)
   DeviceBuffer edges, rois, counts;
   DeviceBuffer packed;          // eight bin indices per voxel (many-ROI histogram path)
@@ -32,7 +33,7 @@ struct Workspace {
   DeviceBuffer crop_img, crop_mask, crop_blur;   // the mask's bounding box as a dense volume (smooth_masked)
   void release_all() {
     DeviceBuffer* all[] = {&a0, &a1, &b0, &b1, &blur, &ckpt, &in_img, &in_mask, &out[0], &out[1],
-                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box, &blur2, &crop_img, &crop_mask, &crop_blur};
+                           &edges, &rois, &counts, &packed, &slab_img, &slab_mask, &box, &blur2, &crop_img, &crop_mask, &crop_blur, &in_i16};
     for (DeviceBuffer* b : all) b->release();
   }
 };
@@ -68,6 +69,7 @@ struct ife_cuda_ctx {
   bool use_async = true;   // cp.async software-pipelined Gaussian passes (option "async_passes")
   bool use_tma = true;     // tensor-map staged, field-per-warp Gaussian passes where the layout allows (option "tma_passes")
   bool use_march4 = true;  // fused feature kernel with four voxels per thread where the layout allows (option "march4")
+  bool host_image_i16 = false;   // host image pointers of the ife_cuda_emphysema_* calls are int16 (option "host_image_i16")
   bool use_box = true;     // masked paths smooth only the mask's support box (option "support_box")
   int* box_host = nullptr; // pinned: the mask extents come back here once per call
   bool overlap_scales = false;   // option "overlap_scales": features of scale s run beside the passes of scale s+1

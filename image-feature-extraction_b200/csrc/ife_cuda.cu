@@ -829,6 +829,40 @@ int stage_in(ife_cuda_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, i
   return IFE_OK;
 }
 
+// int16 -> float on the device (exact).  Option "host_image_i16": the HOST image pointers of the
+// ife_cuda_emphysema_* calls point to int16 voxels -- CT's type on disk, which the reference's tools
+// widen to float on the host while reading (tools/ExtractFeatures.cxx:90-96) -- so a scan's upload
+// is 2 bytes per voxel instead of 4.
+__global__ void widen_i16_kernel(const short* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const short4 v = *reinterpret_cast<const short4*>(in + i4);
+    *reinterpret_cast<float4*>(out + i4) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  } else {
+    for (size_t i = i4; i < n; ++i) out[i] = (float)in[i];
+  }
+}
+
+// upload + widen on stream `st` into `dst` (n floats), through `tmp` (n int16)
+int upload_image_i16(ife_cuda_ctx* ctx, const void* host_i16, void* tmp, float* dst, size_t n, cudaStream_t st) {
+  IFE_CUDA_TRY(ctx, cudaMemcpyAsync(tmp, host_i16, n * sizeof(short), cudaMemcpyHostToDevice, st));
+  const unsigned grid = (unsigned)((n / 4 + 256) / 256);
+  widen_i16_kernel<<<grid, 256, 0, st>>>((const short*)tmp, dst, n);
+  ctx->launches++;
+  IFE_CUDA_TRY(ctx, cudaGetLastError());
+  return IFE_OK;
+}
+
+// the image of an ife_cuda_emphysema_* call: float, or int16 on the host with option "host_image_i16"
+int stage_image(ife_cuda_ctx* ctx, const float* image, size_t n, int mem, const float** dev) {
+  if (mem == IFE_MEM_DEVICE || !ctx->host_image_i16) return stage_in(ctx, ctx->ws.in_img, image, n, mem, dev);
+  IFE_TRY(ctx->ws.in_img.reserve(ctx, n * sizeof(float)));
+  IFE_TRY(ctx->ws.in_i16.reserve(ctx, 2 * ((n + 3) & ~(size_t)3) * sizeof(short)));
+  IFE_TRY(upload_image_i16(ctx, image, ctx->ws.in_i16.ptr, (float*)ctx->ws.in_img.ptr, n, ctx->stream()));
+  *dev = (const float*)ctx->ws.in_img.ptr;
+  return IFE_OK;
+}
+
 }  // namespace ife
 
 using namespace ife;
@@ -940,6 +974,7 @@ int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
   if (std::strcmp(name, "tma_passes") == 0) { ctx->use_tma = value != 0; return IFE_OK; }
   if (std::strcmp(name, "march4") == 0) { ctx->use_march4 = value != 0; return IFE_OK; }
+  if (std::strcmp(name, "host_image_i16") == 0) { ctx->host_image_i16 = value != 0; return IFE_OK; }
   if (std::strcmp(name, "support_box") == 0) { ctx->use_box = value != 0; return IFE_OK; }
   if (std::strcmp(name, "overlap_scales") == 0) { ctx->overlap_scales = value != 0; return IFE_OK; }
   return fail(ctx, IFE_E_INVALID, "unknown option '%s'", name);
@@ -1158,7 +1193,7 @@ int ife_cuda_emphysema_features(ife_cuda_ctx* ctx, const float* image, const uin
   IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
   const float* d_img;
   const uint8_t* d_mask;
-  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_image(ctx, image, n, mem, &d_img));
   IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
   if (mem == IFE_MEM_HOST) {
     // two staging buffers so that the D2H copy of scale s overlaps the kernels of scale s+1
@@ -1242,7 +1277,7 @@ int ife_cuda_emphysema_histograms(ife_cuda_ctx* ctx, const float* image, const u
   IFE_TRY(ctx->ws.blur.reserve(ctx, n * sizeof(float)));
   const float* d_img;
   const uint8_t* d_mask;
-  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_image(ctx, image, n, mem, &d_img));
   IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
 
   const int rows = n_sigma * 8, nb = n_edges + 1, R = std::max(n_roi, 1);
@@ -1350,6 +1385,7 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
     IFE_TRY(img_slot[k]->reserve(ctx, n * sizeof(float)));
     IFE_TRY(mask_slot[k]->reserve(ctx, n));
   }
+  if (ctx->host_image_i16) IFE_TRY(ws.in_i16.reserve(ctx, 2 * ((n + 3) & ~(size_t)3) * sizeof(short)));
   const int rows = n_sigma * 8, nb = n_edges + 1, R = std::max(n_roi, 1);
   const size_t n_counts = (size_t)R * rows * nb;
   IFE_TRY(ws.edges.reserve(ctx, (size_t)rows * n_edges * sizeof(float)));
@@ -1367,7 +1403,10 @@ int ife_cuda_emphysema_histograms_batch(ife_cuda_ctx* ctx, int n_scans, const fl
   auto upload = [&](int i) -> int {
     const int k = i & 1;
     if (i >= 2) IFE_CUDA_TRY(ctx, cudaStreamWaitEvent(cp, ctx->events[2 + k], 0));
-    IFE_CUDA_TRY(ctx, cudaMemcpyAsync(img_slot[k]->ptr, images[i], n * sizeof(float), cudaMemcpyHostToDevice, cp));
+    if (ctx->host_image_i16)
+      IFE_TRY(upload_image_i16(ctx, images[i], (short*)ws.in_i16.ptr + (size_t)k * ((n + 3) & ~(size_t)3), (float*)img_slot[k]->ptr, n, cp));
+    else
+      IFE_CUDA_TRY(ctx, cudaMemcpyAsync(img_slot[k]->ptr, images[i], n * sizeof(float), cudaMemcpyHostToDevice, cp));
     IFE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_slot[k]->ptr, masks[i], n, cudaMemcpyHostToDevice, cp));
     // the mask's support box is reduced right behind its upload, so the host never has to
     // wait for the kernels of the scan before
@@ -1563,7 +1602,7 @@ int ife_cuda_emphysema_feature_samples(ife_cuda_ctx* ctx, const float* image, co
   cudaStream_t st = ctx->stream();
   const float* d_img;
   const uint8_t* d_mask;
-  IFE_TRY(stage_in(ctx, ctx->ws.in_img, image, n, mem, &d_img));
+  IFE_TRY(stage_image(ctx, image, n, mem, &d_img));
   IFE_TRY(stage_in(ctx, ctx->ws.in_mask, mask, n, mem, &d_mask));
   // which voxels: selection flags -> per-tile counts -> offsets (host prefix over a few thousand
   // integers); or an explicit index list

@@ -259,8 +259,9 @@ class Context:
             MEM_HOST))
         return out
 
-    def emphysema_features(self, img, mask, sigmas, spacing=None, out=None):
-        img = np.ascontiguousarray(img, np.float32)
+    def emphysema_features(self, img, mask, sigmas, spacing=None, out=None, _raw_image=False):
+        # _raw_image: pass the image buffer as it is (int16 with option "host_image_i16")
+        img = np.ascontiguousarray(img) if _raw_image else np.ascontiguousarray(img, np.float32)
         mask = np.ascontiguousarray(mask, np.uint8)
         sigmas = list(sigmas)
         if out is None:
@@ -270,8 +271,8 @@ class Context:
             _dn(sigmas), len(sigmas), MEM_HOST))
         return out
 
-    def emphysema_histograms(self, img, mask, sigmas, edges, rois=None, spacing=None):
-        img = np.ascontiguousarray(img, np.float32)
+    def emphysema_histograms(self, img, mask, sigmas, edges, rois=None, spacing=None, _raw_image=False):
+        img = np.ascontiguousarray(img) if _raw_image else np.ascontiguousarray(img, np.float32)
         mask = np.ascontiguousarray(mask, np.uint8)
         sigmas = list(sigmas)
         edges = np.ascontiguousarray(edges, np.float32).reshape(len(sigmas) * 8, -1)
@@ -284,10 +285,10 @@ class Context:
             _ptr(counts), MEM_HOST))
         return counts
 
-    def emphysema_histograms_batch(self, images, masks, sigmas, edges, rois=None, spacing=None):
+    def emphysema_histograms_batch(self, images, masks, sigmas, edges, rois=None, spacing=None, _raw_image=False):
         """images / masks: lists of equally shaped (nz, ny, nx) host arrays (pinned memory makes
         the upload overlap real); rois: (n_scans, R, 6) or None -> counts (n_scans, R|1, S*8, E+1)"""
-        images = [np.ascontiguousarray(a, np.float32) for a in images]
+        images = [np.ascontiguousarray(a) if _raw_image else np.ascontiguousarray(a, np.float32) for a in images]
         masks = [np.ascontiguousarray(m, np.uint8) for m in masks]
         n = len(images)
         sigmas = list(sigmas)

@@ -121,6 +121,12 @@ int ife_cuda_last_work_dims(const ife_cuda_ctx* ctx, int dims[3]);
  * "march4" (default 1): the fused feature kernel owns four x-adjacent voxels per thread when
  * nx % 4 == 0 and the pointers are 16-byte aligned (csrc/features_march4.cuh); 0 selects the
  * one-voxel-per-thread kernel (same results bit for bit).
+ * "host_image_i16" (default 0): the HOST image pointers handed to ife_cuda_emphysema_features /
+ * _histograms / _histograms_batch / _feature_samples point to int16 voxels (cast the pointer) -- CT's
+ * type on disk, which the reference's tools widen to float on the host while reading
+ * (tools/ExtractFeatures.cxx:90-96).  The library uploads 2 bytes per voxel and widens on the device
+ * (exact); a batch of scans whose kernels take less time than a float upload becomes kernel-bound.
+ * Device pointers are always float.
  * "overlap_scales" (default 0): device-resident ife_cuda_emphysema_features calls with several
  * scales run the Gaussian passes one scale ahead on a high-priority stream of the context,
  * beside the fused feature kernel of the scale before (two blur buffers); same results bit

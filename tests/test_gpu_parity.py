@@ -544,6 +544,33 @@ def test_workspace_growth_between_host_calls(oracle):
         c.close()
 
 
+def test_int16_host_images(ctx):
+    """Option host_image_i16: the host image pointer is int16 (CT's type on disk); the upload is 2
+    bytes per voxel and the widening to float happens on the device.  Same results as the float
+    upload of the same values, for the feature volumes, the histograms and a batch (odd voxel
+    counts included: the second upload slot of a batch must stay aligned)."""
+    for shape in ((24, 40, 64), (9, 13, 37)):
+        img16 = np.round(synth.ct_like(shape, seed=81, n_blobs=6)).astype(np.int16)
+        imgf = img16.astype(np.float32)
+        mask = synth.clamp01(synth.lung_mask(shape))
+        sig = [0.6, 2.4]
+        ref = ctx.emphysema_features(imgf, mask, sig)
+        edges = np.stack([synth.equalized_edges(ref[s, k][mask != 0], 12) for s in range(2) for k in range(8)])
+        ref_counts = ctx.emphysema_histograms(imgf, mask, sig, edges)
+        ref_batch = ctx.emphysema_histograms_batch([imgf, imgf[::-1].copy(), imgf], [mask, mask[::-1].copy(), mask], sig, edges)
+        ctx.set_option("host_image_i16", 1)
+        try:
+            as_f32_ptr = img16.view(np.int16)          # the binding passes the buffer's address; dtype is not checked by the C ABI
+            got = ctx.emphysema_features(as_f32_ptr, mask, sig, _raw_image=True)
+            got_counts = ctx.emphysema_histograms(as_f32_ptr, mask, sig, edges, _raw_image=True)
+            got_batch = ctx.emphysema_histograms_batch([img16, img16[::-1].copy(), img16], [mask, mask[::-1].copy(), mask], sig, edges, _raw_image=True)
+        finally:
+            ctx.set_option("host_image_i16", 0)
+        assert bits_equal(got, ref)
+        assert np.array_equal(got_counts, ref_counts)
+        assert np.array_equal(got_batch, ref_batch)
+
+
 def test_bad_arguments_are_rejected(ctx):
     import ctypes
     import ife_b200
