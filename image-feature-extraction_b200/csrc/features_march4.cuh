@@ -259,10 +259,12 @@ features_march4_kernel(const __grid_constant__ StencilCoef S, const __grid_const
           }
         }
       }
+      if (!(inside[0] && inside[1] && inside[2] && inside[3])) {   // rare inside a mask, never without one
 #pragma unroll
-      for (int i = 0; i < kQV; ++i)
+        for (int i = 0; i < kQV; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[i][k] = inside[i] ? f[i][k] : 0.0f;
+          for (int k = 0; k < 8; ++k) f[i][k] = inside[i] ? f[i][k] : 0.0f;
+      }
     }
 
     if (in_xy) {
