@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -235,12 +236,39 @@ int make_map3(ife_cuda_ctx* ctx, CUtensorMap* m, const void* base, bool u8, long
 #define IFE_TMA_MINB_X 8
 #endif
 
+// How many blocks per SM a tensor-map pass should run with: the largest count the kernel's own
+// resources allow (`fit`), or one or two fewer when that needs fewer rounds per resident block
+// (cost model: rounds x blocks per SM, the passes being throughput-bound).  Measured: the model does
+// not hold -- z 10 vs 11: 0.562 / 0.563 ms, y 11 vs 12: 0.586 / 0.578, x 7 vs 8: 0.546 / 0.560 -- latency
+// hiding matters as much as the last round, so the option "tma_balance" is off by default.  IFE_TMA_BLOCKS_{Z,Y,X}
+// in the environment overrides (experiments).  0 = leave the request alone.
+int tma_blocks_per_sm(const ife_cuda_ctx* ctx, int axis, long long blocks, int smem_need) {
+  static const char* names[3] = {"IFE_TMA_BLOCKS_Z", "IFE_TMA_BLOCKS_Y", "IFE_TMA_BLOCKS_X"};
+  if (const char* e = std::getenv(names[axis])) return std::atoi(e);
+  if (!ctx->tma_balance) return 0;
+  const int fit = std::min(axis == AX_X ? IFE_TMA_MINB_X : (axis == AX_Z ? IFE_TMA_MINB_Z : IFE_TMA_MINB_S),
+                           233472 / (smem_need + 1024));
+  int best = fit;
+  long long best_cost = -1;
+  for (int b = fit; b >= std::max(1, fit - 2); --b) {
+    const long long slots = (long long)b * ctx->sm_count;
+    const long long cost = ((blocks + slots - 1) / slots) * b;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = b; }
+  }
+  return best == fit ? 0 : best;
+}
+
 template <int AXIS, int INMODE, bool DIVIDE>
 int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0, const CUtensorMap& i1,
                     const CUtensorMap& o0, const CUtensorMap& o1, const TmaArgs& A, dim3 grid) {
   constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X : (INMODE == IN_IMG_U8 ? IFE_TMA_MINB_Z : IFE_TMA_MINB_S);
-  constexpr size_t smem = (INMODE == IN_IMG_U8 ? kRegionImgU8 + kRegionU8 + kOnesTile
-                                               : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) + kTmaBarBytes;
+  constexpr size_t smem_need = (INMODE == IN_IMG_U8 ? kRegionImgU8 + kRegionU8 + kOnesTile
+                                                    : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) + kTmaBarBytes;
+  // Blocks per SM: all blocks of a pass take the same time, so the pass costs ceil(blocks / slots)
+  // rounds.  Where one block per SM fewer turns a nearly empty last round into a full one, the
+  // shared memory request is padded so that exactly `want` blocks fit (tma_blocks_per_sm()).
+  const int want = tma_blocks_per_sm(ctx, AXIS, (long long)grid.x * grid.y, (int)smem_need);
+  const size_t smem = want > 0 ? std::max<size_t>(smem_need, (size_t)(233472 / want - 1024) / 128 * 128) : smem_need;
   if (ctx->arith == IFE_ARITH_FMA) {
     auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, true, MINB>;
     IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -974,6 +1002,7 @@ int ife_cuda_set_option(ife_cuda_ctx* ctx, const char* name, int value) {
   if (std::strcmp(name, "async_passes") == 0) { ctx->use_async = value != 0; return IFE_OK; }
   if (std::strcmp(name, "tma_passes") == 0) { ctx->use_tma = value != 0; return IFE_OK; }
   if (std::strcmp(name, "march4") == 0) { ctx->use_march4 = value != 0; return IFE_OK; }
+  if (std::strcmp(name, "tma_balance") == 0) { ctx->tma_balance = value != 0; return IFE_OK; }
   if (std::strcmp(name, "host_image_i16") == 0) { ctx->host_image_i16 = value != 0; return IFE_OK; }
   if (std::strcmp(name, "support_box") == 0) { ctx->use_box = value != 0; return IFE_OK; }
   if (std::strcmp(name, "overlap_scales") == 0) { ctx->overlap_scales = value != 0; return IFE_OK; }
