@@ -357,6 +357,29 @@ def test_support_box_is_invisible(ctx, oracle):
     assert np.array_equal(both[1], ctx.emphysema_histograms(img, corner, sigmas, edges))
 
 
+def test_support_box_finite_input_precondition(ctx):
+    """include/ife_cuda.h documents the one way option "support_box" can change a result: a NaN
+    voxel OUTSIDE the mask's box.  The full-volume path multiplies it by the zero certainty
+    (0 * NaN = NaN) and the recursion carries it into the mask, as the reference would; the
+    cropped path never reads it and gives the result of the image with that voxel cleared."""
+    shape = (40, 64, 96)
+    img = synth.ct_like(shape, seed=33, n_blobs=8)
+    zz, yy, xx = np.ogrid[:shape[0], :shape[1], :shape[2]]
+    mask = (((zz - 20) / 6.0) ** 2 + ((yy - 30) / 9.0) ** 2 + ((xx - 40) / 11.0) ** 2 <= 1).astype(np.uint8)
+    bad = img.copy()
+    bad[20, 30, 90] = np.nan                     # same row as the blob's centre, far outside its box
+    clean = img.copy()
+    clean[20, 30, 90] = 0.0
+    with_box = ctx.emphysema_features(bad, mask, [1.2])
+    assert np.isfinite(with_box).all() and bits_equal(with_box, ctx.emphysema_features(clean, mask, [1.2]))
+    ctx.set_option("support_box", 0)
+    try:
+        full = ctx.emphysema_features(bad, mask, [1.2])
+    finally:
+        ctx.set_option("support_box", 1)
+    assert np.isnan(full[0, 0][mask != 0]).any()  # the reference's behaviour: the NaN reaches in-mask voxels
+
+
 def test_overlap_scales_same_results(ctx):
     """Option overlap_scales (device-resident calls): the Gaussian passes run one scale ahead
     on a second stream, the feature kernel of the scale before beside them, two blur buffers
