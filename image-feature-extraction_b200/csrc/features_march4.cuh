@@ -166,11 +166,18 @@ features_march4_kernel(const __grid_constant__ StencilCoef S, const __grid_const
     for (int i = 0; i < kQV; ++i) {
       inside[i] = in_xy && ((m_cur >> (8 * i)) & 0xffu) != 0u;
       any_inside = any_inside || inside[i];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[i][k] = 0.0f;
     }
 
-    if (any_inside) {
+    if (!any_inside) {
+#pragma unroll
+      for (int i = 0; i < kQV; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[i][k] = 0.0f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kQV; ++i)
+#pragma unroll
+        for (int k = NFEAT; k < 8; ++k) f[i][k] = 0.0f;   // slots this mode never writes
       float a[6], b[6], c[6], bm[6], bn[6];
       row6(pC, b);
       row6(pP, bm);
