@@ -182,10 +182,12 @@ size_t ckpt_bytes(int nf, int n, size_t n_lines) {
 
 size_t ckpt_bytes_volume(int nf, int nx, int ny, int nz) {
   // lines padded to whole tiles of 32 (the tensor-map kernels checkpoint every lane of a tile)
+  // one field: two stacks of ceil(rows / 2) rows each (smooth_volume), i.e. up to one row more
   const size_t px = (size_t)(nx + 31) / 32 * 32, py = (size_t)(ny + 31) / 32 * 32;
-  const size_t a = ckpt_bytes(nf, nz, px * ny);
-  const size_t b = ckpt_bytes(nf, nx, py * nz);
-  const size_t c = ckpt_bytes(nf, ny, px * nz);
+  const size_t ry = (size_t)ny + (nf == 1), rz = (size_t)nz + (nf == 1);
+  const size_t a = ckpt_bytes(nf, nz, px * ry);
+  const size_t b = ckpt_bytes(nf, nx, py * rz);
+  const size_t c = ckpt_bytes(nf, ny, px * rz);
   return std::max(a, std::max(b, c));
 }
 
@@ -293,6 +295,15 @@ bool tma_passes_usable(const ife_cuda_ctx* ctx, const float* in0, const void* ce
   if (nx % 16 != 0 || ny >= 65536 || nzb >= 65536) return false;   // 16-byte row pitch of the uint8 mask; grid.y
   auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   return al(in0) && al(cert) && al(out0) && encode_tiled_fn() != nullptr;
+}
+
+// ... and the one-field smoothing (plain Gaussian)?  Rows of 16-byte multiples for the maps' strides.
+bool tma_gaussian_usable(const ife_cuda_ctx* ctx, const float* in0, const void* cert, const float* out0, int nx, int ny,
+                         int nzb, const uint8_t* outmask_u8, const float* outmask_f32) {
+  if (!ctx->use_tma || cert || outmask_u8 || outmask_f32) return false;
+  if (nx % 4 != 0 || ny >= 2 * 65535 || nzb >= 2 * 65535) return false;
+  auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  return al(in0) && al(out0) && encode_tiled_fn() != nullptr;
 }
 
 constexpr int kAsyncStages = 3;
@@ -434,7 +445,7 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
       IFE_TRY(make_map3(ctx, &mo1, a1, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
       T.in0 = in0; T.in1 = cert;
       T.s_lane = 1; T.s_bx = 32; T.s_by = nx; T.s_n = plane; T.lanes_total = nx;
-      T.n = nzb; T.out_lo = kz0; T.out_hi = kz1;
+      T.n = nzb; T.out_lo = kz0; T.out_hi = kz1; T.rows1 = ny;
       ProfScope prof(ctx, K_PASS_Z);
       IFE_TRY((launch_tma_pass<AX_Z, IN_IMG_U8, false>(ctx, cz, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, ny))));
     }
@@ -445,7 +456,7 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
       IFE_TRY(make_map3(ctx, &mo1, b1 + boff, false, nx, ny, nzk, 4LL * nx, 4 * plane, kTL, 32, 1, true));
       T.in0 = a0 + koff; T.in1 = a1 + koff;
       T.s_lane = nx; T.s_bx = 32LL * nx; T.s_by = plane; T.s_n = 1; T.lanes_total = ny;
-      T.n = nx; T.out_lo = 0; T.out_hi = nx;
+      T.n = nx; T.out_lo = 0; T.out_hi = nx; T.rows1 = nzk;
       ProfScope prof(ctx, K_PASS_X);
       IFE_TRY((launch_tma_pass<AX_X, IN_FIELDS, false>(ctx, cx, mi0, mi1, mo0, mo1, T, dim3((ny + 31) / 32, nzk))));
     }
@@ -457,9 +468,62 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
       IFE_TRY(make_map3(ctx, &mo0, out0 + yoff, false, wx, ny, nzk, 4LL * nx, 4 * plane, 32, kTL, 1, false));
       T.in0 = b0 + yoff; T.in1 = b1 + yoff;
       T.s_lane = 1; T.s_bx = 32; T.s_by = plane; T.s_n = nx; T.lanes_total = wx;
-      T.n = ny; T.out_lo = ky0; T.out_hi = ky1;
+      T.n = ny; T.out_lo = ky0; T.out_hi = ky1; T.rows1 = nzk;
       ProfScope prof(ctx, K_PASS_Y);
       IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, true>(ctx, cy, mi0, mi1, mo0, mo0, T, dim3((wx + 31) / 32, nzk))));
+    }
+    return IFE_OK;
+  }
+
+  if (tma_gaussian_usable(ctx, in0, cert, out0, nx, ny, nzb, outmask_u8, outmask_f32)) {
+    // One field (the plain smoothing Gaussian) through the same kernels: the second warp of a block,
+    // which carries field c in the normalized convolution, takes a second stack of rows instead --
+    // the upper half of the y rows in the z pass, the upper half of the planes in the x and y passes.
+    // Its tensor maps are views of that half, so the kernels see two independent "fields".
+    const long long plane = (long long)nx * ny;
+    const int nzk = kz1 - kz0;
+    const size_t koff = (size_t)kz0 * plane, boff = (size_t)(kz0 - keep0) * plane;
+    CUtensorMap mi0, mi1, mo0, mo1;
+    TmaArgs T;
+    std::memset(&T, 0, sizeof(T));
+    T.ckpt = (double*)ws.ckpt.ptr;
+    {   // z pass: rows [0, h) and [h, ny)
+      const int h = (ny + 1) / 2, h1 = ny - h;   // h1 >= 2
+      const size_t off1 = (size_t)h * nx;
+      IFE_TRY(make_map3(ctx, &mi0, in0, false, nx, h, nzb, 4LL * nx, 4 * plane, 32, 1, kTRows, false));
+      IFE_TRY(make_map3(ctx, &mi1, in0 + off1, false, nx, h1, nzb, 4LL * nx, 4 * plane, 32, 1, kTRows, false));
+      IFE_TRY(make_map3(ctx, &mo0, a0, false, nx, h, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
+      IFE_TRY(make_map3(ctx, &mo1, a0 + off1, false, nx, h1, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
+      T.in0 = in0; T.in1 = in0 + off1;
+      T.s_lane = 1; T.s_bx = 32; T.s_by = nx; T.s_n = plane; T.lanes_total = nx;
+      T.n = nzb; T.out_lo = kz0; T.out_hi = kz1; T.rows1 = h1;
+      ProfScope prof(ctx, K_PASS_Z);
+      IFE_TRY((launch_tma_pass<AX_Z, IN_FIELDS, false>(ctx, cz, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, h))));
+    }
+    const int h = (nzk + 1) / 2, h1 = nzk - h;   // x and y passes: planes [0, h) and [h, nzk) of the kept range
+    const int m1 = std::max(h1, 1);              // a map needs a non-empty extent even when nobody uses it
+    const size_t off1 = (size_t)h * plane;
+    {   // x pass
+      IFE_TRY(make_map3(ctx, &mi0, a0 + koff, false, nx, ny, h, 4LL * nx, 4 * plane, kXRow, 32, 1, false));
+      IFE_TRY(make_map3(ctx, &mi1, a0 + koff + off1, false, nx, ny, m1, 4LL * nx, 4 * plane, kXRow, 32, 1, false));
+      IFE_TRY(make_map3(ctx, &mo0, b0 + boff, false, nx, ny, h, 4LL * nx, 4 * plane, kTL, 32, 1, true));
+      IFE_TRY(make_map3(ctx, &mo1, b0 + boff + off1, false, nx, ny, m1, 4LL * nx, 4 * plane, kTL, 32, 1, true));
+      T.in0 = a0 + koff; T.in1 = a0 + koff + off1;
+      T.s_lane = nx; T.s_bx = 32LL * nx; T.s_by = plane; T.s_n = 1; T.lanes_total = ny;
+      T.n = nx; T.out_lo = 0; T.out_hi = nx; T.rows1 = h1;
+      ProfScope prof(ctx, K_PASS_X);
+      IFE_TRY((launch_tma_pass<AX_X, IN_FIELDS, false>(ctx, cx, mi0, mi1, mo0, mo1, T, dim3((ny + 31) / 32, h))));
+    }
+    {   // y pass, straight into the result
+      IFE_TRY(make_map3(ctx, &mi0, b0 + boff, false, nx, ny, h, 4LL * nx, 4 * plane, 32, kTRows, 1, false));
+      IFE_TRY(make_map3(ctx, &mi1, b0 + boff + off1, false, nx, ny, m1, 4LL * nx, 4 * plane, 32, kTRows, 1, false));
+      IFE_TRY(make_map3(ctx, &mo0, out0 + boff, false, nx, ny, h, 4LL * nx, 4 * plane, 32, kTL, 1, false));
+      IFE_TRY(make_map3(ctx, &mo1, out0 + boff + off1, false, nx, ny, m1, 4LL * nx, 4 * plane, 32, kTL, 1, false));
+      T.in0 = b0 + boff; T.in1 = b0 + boff + off1;
+      T.s_lane = 1; T.s_bx = 32; T.s_by = plane; T.s_n = nx; T.lanes_total = nx;
+      T.n = ny; T.out_lo = ky0; T.out_hi = ky1; T.rows1 = h1;
+      ProfScope prof(ctx, K_PASS_Y);
+      IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, false>(ctx, cy, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, h))));
     }
     return IFE_OK;
   }

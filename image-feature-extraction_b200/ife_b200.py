@@ -371,6 +371,10 @@ class Context:
             len(sigmas), _ptr(edges), edges.shape[1], _ptr(r), 0 if r is None else r.shape[0],
             _ptr(counts_ptr), MEM_DEVICE))
 
+    def gaussian_dev(self, img_ptr, out_ptr, dims, sigma, spacing=None):
+        self._check(self.L.ife_cuda_gaussian(self.h, _ptr(img_ptr), _ptr(out_ptr), _i3(dims), _d3(spacing),
+                                             sigma, MEM_DEVICE))
+
     def hessian_eigen_features_dev(self, img_ptr, mask_ptr, out_ptr, dims, sigma, spacing=None,
                                    flags=0):
         self._check(self.L.ife_cuda_hessian_eigen_features(

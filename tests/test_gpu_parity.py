@@ -161,6 +161,37 @@ def test_tensor_map_passes_bit_exact(ctx, oracle, arith):
         ctx.set_arith(1)
 
 
+@pytest.mark.parametrize("arith", [1, 0])
+def test_tensor_map_plain_gaussian_bit_exact(ctx, oracle, arith):
+    """One field through the tensor-map kernels (nx % 4 == 0): the second warp of a block takes a
+    second stack of rows (upper half of y in the z pass, upper half of the planes in the x and y
+    passes).  Odd row / plane counts (the halves differ by one), ragged tiles, short lines."""
+    shapes = [((40, 64, 96), 1.2), ((37, 45, 48), 2.4), ((4, 4, 16), 0.6), ((5, 7, 32), 1.0), ((16, 16, 16), 4.8),
+              ((33, 31, 64), 0.6), ((19, 70, 84), 1.0), ((130, 21, 20), 4.8), ((9, 5, 4), 0.6)]
+    ctx.set_arith(arith)
+    try:
+        for shape, sigma in shapes:      # shape = (nz, ny, nx)
+            img = synth.ct_like(shape, seed=sum(shape) + 1, n_blobs=6)
+            got = ctx.gaussian(img, sigma)
+            ctx.set_option("tma_passes", 0)
+            try:
+                old = ctx.gaussian(img, sigma)
+            finally:
+                ctx.set_option("tma_passes", 1)
+            n, worst = mismatch_report(got, old)
+            assert n == 0, "%s sigma=%g: %d values differ from the cp.async passes (max %g)" % (shape, sigma, n, worst)
+            if np.prod(shape) < 200_000:
+                ref = oracle.smoothing_recursive_gaussian(img, sigma, arith=arith)
+                assert mismatch_report(got, ref)[0] == 0, "%s sigma=%g vs oracle" % (shape, sigma)
+        # anisotropic spacing, and the consumer of the plain Gaussian: Hessian eigen features at sigma > 0
+        shape = (21, 40, 64)
+        img = synth.ct_like(shape, seed=8, n_blobs=5)
+        sp = (0.7, 0.7, 1.3)
+        assert mismatch_report(ctx.gaussian(img, 1.1, spacing=sp), oracle.smoothing_recursive_gaussian(img, 1.1, spacing=sp, arith=arith))[0] == 0
+    finally:
+        ctx.set_arith(1)
+
+
 def test_normalized_gaussian_zero_divisor_rule(ctx, oracle):
     # certainty identically zero -> G(c) == 0 -> itk::DivideImageFilter yields float max
     img = synth.ct_like((8, 8, 8), seed=1, n_blobs=2)
