@@ -9,8 +9,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <sys/mman.h>
 
 #include <cuda_runtime.h>
 
@@ -1015,10 +1021,64 @@ const char* ife_cuda_last_error(const ife_cuda_ctx* ctx) {
   return ctx ? ctx->error.c_str() : "null context";
 }
 
+// Page-locked host memory.  cudaHostAlloc costs 0.48 s per GB on the B200 boxes (the driver faults
+// and zeroes 4 KB pages on one core): 6 s for the 13.4 GB of feature volumes one ExtractFeatures run
+// holds, against 0.3 s of GPU work.  Large blocks are therefore mapped anonymously with transparent huge
+// pages, faulted in by all cores, and registered with the driver: 0.043 s per GB, the same 57 GB/s of
+// D2H rate (profiles/micro/pin_alloc.cu).  Anything that fails falls back to cudaHostAlloc.
+namespace {
+struct MappedBlock { void* base; size_t len; };
+std::mutex g_mapped_mu;
+std::map<void*, MappedBlock> g_mapped;   // user pointer -> mapping
+constexpr size_t kHugePage = (size_t)2 << 20;
+
+void* host_alloc_mapped(size_t bytes) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {   // nothing to register with
+    cudaGetLastError();
+    return nullptr;
+  }
+  const auto t_begin = std::chrono::steady_clock::now();
+  const size_t len = (bytes + 2 * kHugePage - 1) / kHugePage * kHugePage;   // room to align the start to 2 MB
+  void* base = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (base == MAP_FAILED) return nullptr;
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + kHugePage - 1) / kHugePage * kHugePage);
+  madvise(p, bytes, MADV_HUGEPAGE);   // advisory: without it the touch below just faults 4 KB pages
+  int n_threads = (int)std::thread::hardware_concurrency();
+  n_threads = std::max(1, std::min(n_threads, std::min(32, (int)(bytes / (64u << 20)) + 1)));
+  const size_t per = (bytes / n_threads + 4095) / 4096 * 4096;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_threads; ++t)
+    pool.emplace_back([=] {
+      const size_t a = (size_t)t * per, b = std::min(bytes, a + per);
+      for (size_t i = a; i < b; i += 4096) reinterpret_cast<volatile char*>(p)[i] = 0;
+    });
+  for (auto& t : pool) t.join();
+  const auto t_touch = std::chrono::steady_clock::now();
+  const cudaError_t reg = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (std::getenv("IFE_ALLOC_TRACE"))
+    std::fprintf(stderr, "[ife] host_alloc %zu MB: map + touch (%d threads) %.3f s, register %.3f s (%s)\n", bytes >> 20, n_threads,
+                 std::chrono::duration<double>(t_touch - t_begin).count(),
+                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_touch).count(), cudaGetErrorString(reg));
+  if (reg != cudaSuccess) {
+    cudaGetLastError();
+    munmap(base, len);
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_mapped_mu);
+  g_mapped[p] = MappedBlock{base, len};
+  return p;
+}
+}  // namespace
+
 int ife_cuda_host_alloc(size_t bytes, void** ptr) {
   if (!ptr) return IFE_E_INVALID;
   *ptr = nullptr;
   if (bytes == 0) return IFE_OK;
+  if (bytes >= ((size_t)32 << 20) && !std::getenv("IFE_NO_MAPPED_HOST_ALLOC")) {
+    *ptr = host_alloc_mapped(bytes);
+    if (*ptr) return IFE_OK;
+  }
   if (cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) != cudaSuccess) {
     cudaGetLastError();   // not sticky: the caller falls back to pageable memory
     *ptr = nullptr;
@@ -1028,7 +1088,19 @@ int ife_cuda_host_alloc(size_t bytes, void** ptr) {
 }
 
 void ife_cuda_host_free(void* ptr) {
-  if (ptr) cudaFreeHost(ptr);
+  if (!ptr) return;
+  MappedBlock blk{nullptr, 0};
+  {
+    std::lock_guard<std::mutex> lk(g_mapped_mu);
+    auto it = g_mapped.find(ptr);
+    if (it != g_mapped.end()) { blk = it->second; g_mapped.erase(it); }
+  }
+  if (blk.base) {
+    cudaHostUnregister(ptr);
+    munmap(blk.base, blk.len);
+  } else {
+    cudaFreeHost(ptr);
+  }
 }
 
 int ife_cuda_set_stream(ife_cuda_ctx* ctx, void* s) {

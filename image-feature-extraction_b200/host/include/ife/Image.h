@@ -13,6 +13,7 @@
 #define IFE_B200_IMAGE_H
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +35,9 @@ struct Geometry {
   size_t voxels() const { return (size_t)size[0] * size[1] * size[2]; }
 };
 
+// seconds spent allocating (page-locking) pixel storage so far in this process
+inline double& alloc_seconds() { static double s = 0.0; return s; }
+
 // Contiguous host storage: page-locked when the library can provide it, pageable otherwise
 // (no GPU: the IO classes still work).  Growth leaves new elements uninitialised.
 template <typename T>
@@ -53,7 +57,10 @@ public:
       release();
       if (n) {
         void* p = nullptr;
-        if (ife_cuda_host_alloc(n * sizeof(T), &p) == IFE_OK && p) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = ife_cuda_host_alloc(n * sizeof(T), &p);
+        alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rc == IFE_OK && p) {
           m_Pinned = true;
         } else {
           p = std::malloc(n * sizeof(T));

@@ -94,7 +94,9 @@ int main(int argc, char* argv[]) {
     }
   }
   if (std::getenv("IFE_TIMING"))
-    std::cerr << "[timing] ife_cuda_emphysema_features(IFE_MEM_HOST, page-locked buffers, " << scales.size()
+    std::cerr << "[timing] writing " << scales.size() * featureNames.size() << " " << OUT_FILE_TYPE << " files: "
+              << ife::nifti::write_seconds() << " s; reading: " << ife::nifti::read_seconds()
+              << " s; page-locked allocation: " << ife::alloc_seconds() << " s; ife_cuda_emphysema_features(IFE_MEM_HOST, page-locked buffers, " << scales.size()
               << " scales): " << featureFilter->GetLastCallSeconds() << " s" << std::endl;
   return EXIT_SUCCESS;
 }

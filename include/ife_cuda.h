@@ -79,7 +79,11 @@ const char* ife_cuda_last_error(const ife_cuda_ctx* ctx);
  * host<->device copies of such a buffer run at full PCIe rate and overlap with the kernels
  * (a pageable buffer is staged by the driver, synchronously).  No context needed; fails with
  * IFE_E_CUDA without a device (callers then fall back to malloc).  The C++ facades allocate every
- * image this way (host/include/ife/Image.h). */
+ * image this way (host/include/ife/Image.h).  Blocks of 32 MB and more are anonymous huge-page
+ * mappings faulted in by all cores and registered with the driver (0.05 s per GB instead of
+ * cudaHostAlloc's 0.4-0.5); IFE_NO_MAPPED_HOST_ALLOC in the environment forces cudaHostAlloc,
+ * IFE_ALLOC_TRACE prints the time of every large allocation to stderr.  Free with
+ * ife_cuda_host_free only. */
 int ife_cuda_host_alloc(size_t bytes, void** ptr);
 void ife_cuda_host_free(void* ptr);
 /* Use an existing cudaStream_t (e.g. a framework's current stream) instead of the

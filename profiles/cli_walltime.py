@@ -24,4 +24,6 @@ p = subprocess.run([exe, "-i", d + "/img.nii", "-m", d + "/mask.nii", "-o", d + 
 dt = time.time() - t0
 n_out = len([f for f in os.listdir(d) if f.startswith("f_scale")])
 print("ExtractFeatures 512x512x%d, 4 scales: rc=%d, %d files, total wall %.1f s; %s" % (nz, p.returncode, n_out, dt, p.stderr.strip().splitlines()[-1] if p.stderr.strip() else ""))
+if os.environ.get("IFE_ALLOC_TRACE"):
+    print("\n".join(l for l in p.stderr.splitlines() if l.startswith("[ife]")))
 shutil.rmtree(d)
