@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -47,15 +48,37 @@ inline bool ends_with(const std::string& s, const std::string& e) {
   return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0;
 }
 
+// IFE_IO_THREADS in the environment sets the thread count of the reader's conversion and of the
+// .nii.gz writer (default: the hardware's, at most 32).
+inline int io_threads(size_t pieces) {
+  int t = (int)std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("IFE_IO_THREADS")) t = std::atoi(e);
+  t = std::max(1, std::min(t, 32));
+  return (int)std::min<size_t>((size_t)t, std::max<size_t>(pieces, 1));
+}
+
+
 template <typename TOut, typename TIn>
-void convert(const std::vector<unsigned char>& raw, bool swapped, double slope, double inter, TOut* out, size_t n) {
-  const bool scale = slope != 0.0 && !(slope == 1.0 && inter == 0.0);
-  for (size_t i = 0; i < n; ++i) {
+void convert_range(const unsigned char* raw, bool swapped, bool scale, double slope, double inter, TOut* out, size_t a, size_t b) {
+  for (size_t i = a; i < b; ++i) {
     TIn v;
-    std::memcpy(&v, raw.data() + i * sizeof(TIn), sizeof(TIn));
+    std::memcpy(&v, raw + i * sizeof(TIn), sizeof(TIn));
     if (swapped) swap_bytes(&v, sizeof(TIn), 1);
     out[i] = scale ? static_cast<TOut>((double)v * slope + inter) : static_cast<TOut>(v);
   }
+}
+
+// raw voxels -> pixel type, on all cores (a 512x512x400 scan is 105 M voxels)
+template <typename TOut, typename TIn>
+void convert(const unsigned char* raw, bool swapped, double slope, double inter, TOut* out, size_t n) {
+  const bool scale = slope != 0.0 && !(slope == 1.0 && inter == 0.0);
+  const int n_threads = io_threads(n >> 22);
+  if (n_threads <= 1) { convert_range<TOut, TIn>(raw, swapped, scale, slope, inter, out, 0, n); return; }
+  std::vector<std::thread> pool;
+  const size_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t)
+    pool.emplace_back([=] { convert_range<TOut, TIn>(raw, swapped, scale, slope, inter, out, std::min(n, t * per), std::min(n, (t + 1) * per)); });
+  for (auto& t : pool) t.join();
 }
 
 // seconds spent inside Read() / Write() so far in this process (the tools print them under IFE_TIMING)
@@ -115,16 +138,18 @@ typename Image<T>::Pointer Read(const std::string& path) {
   std::vector<unsigned char> junk(skip > 0 ? skip : 1);
   if (skip > 0 && gzread(f, junk.data(), (unsigned)skip) != skip) { gzclose(f); throw std::runtime_error("'" + path + "': truncated"); }
   const size_t n = g.voxels();
-  std::vector<unsigned char> raw(n * bpv);
+  const size_t raw_bytes = n * bpv;
+  std::unique_ptr<unsigned char[]> raw_store(new unsigned char[raw_bytes ? raw_bytes : 1]);   // not zero-filled
+  const unsigned char* raw = raw_store.get();
   size_t got = 0;
-  while (got < raw.size()) {
-    const unsigned want = (unsigned)std::min<size_t>(raw.size() - got, 1u << 30);
-    const int r = gzread(f, raw.data() + got, want);
+  while (got < raw_bytes) {
+    const unsigned want = (unsigned)std::min<size_t>(raw_bytes - got, 1u << 30);
+    const int r = gzread(f, raw_store.get() + got, want);
     if (r <= 0) break;
     got += (size_t)r;
   }
   gzclose(f);
-  if (got != raw.size()) throw std::runtime_error("'" + path + "': truncated voxel data");
+  if (got != raw_bytes) throw std::runtime_error("'" + path + "': truncated voxel data");
   T* out = img->GetBufferPointer();
   switch (datatype) {
     case DT_UINT8: convert<T, uint8_t>(raw, swapped, slope, inter, out, n); break;
@@ -145,14 +170,6 @@ typename Image<T>::Pointer Read(const std::string& path) {
 // header, and the CRC-32 of the whole is combined from the pieces'.  Any gzip reader sees an
 // ordinary .gz file.  The 32 feature volumes of one ExtractFeatures run are 13 GB of floats:
 // with one zlib stream the tool spent 75 s writing them and 0.4 s computing them.
-// IFE_IO_THREADS in the environment sets the thread count (default: the hardware's, at most 32).
-inline int io_threads(size_t pieces) {
-  int t = (int)std::thread::hardware_concurrency();
-  if (const char* e = std::getenv("IFE_IO_THREADS")) t = std::atoi(e);
-  t = std::max(1, std::min(t, 32));
-  return (int)std::min<size_t>((size_t)t, std::max<size_t>(pieces, 1));
-}
-
 inline void gz_write_parallel(const std::string& path, const unsigned char* head, size_t head_bytes,
                               const unsigned char* data, size_t bytes) {
   const size_t kPiece = (size_t)8 << 20;
