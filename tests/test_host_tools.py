@@ -22,6 +22,26 @@ def test_host_selftest(tmp_path):
     assert p.returncode == 0, p.stdout + p.stderr
 
 
+def test_multithreaded_gzip_writer_makes_an_ordinary_gz_file(tmp_path):
+    """The .nii.gz writer deflates 8 MB pieces on several threads and joins them into ONE gzip member
+    (ife/IO/NiftiIO.h, gz_write_parallel): Python's gzip and `gzip -t` must read it like any other."""
+    import gzip
+    import zlib
+    p = run("ife_host_selftest", str(tmp_path), "keep")       # leaves the 21 MB, three-piece volume behind
+    assert p.returncode == 0, p.stdout + p.stderr
+    path = os.path.join(str(tmp_path), "ife_selftest_big.nii.gz")
+    blob = open(path, "rb").read()
+    assert blob[:4] == b"\x1f\x8b\x08\x00"
+    raw = gzip.decompress(blob)
+    assert len(raw) == 352 + 256 * 160 * 131 * 4
+    assert int.from_bytes(blob[-8:-4], "little") == zlib.crc32(raw)           # the combined CRC-32 of the pieces
+    assert int.from_bytes(blob[-4:], "little") == len(raw) % (1 << 32)
+    vol, _ = nifti_util.read(path)
+    assert vol.shape == (131, 160, 256) and vol.dtype == np.float32
+    flat = vol.ravel()
+    assert np.all(flat[:1024] == 0) and np.all(flat[4096:4096 + 1024] == 0) and flat[2000] != 0
+
+
 @pytest.mark.parametrize("tool,required", [("ExtractFeatures", "-i -m -o -s"),
                                            ("MaskedNormalizedConvolution", "-i -c -s -o"),
                                            ("FiniteDifference_HessianFeatures", "-i -m -o"),
