@@ -13,6 +13,7 @@
 #define IFE_B200_IMAGE_TO_EMPHYSEMA_FEATURES_FILTER_H
 #include <chrono>
 #include <memory>
+#include <future>
 #include <vector>
 
 #include "ife/Context.h"
@@ -50,8 +51,12 @@ public:
 
   void Update() {
     if (!m_Image || !m_Mask) throw ExceptionObject(IFE_E_INVALID, "ImageToEmphysemaFeaturesFilter: inputs not set");
-    m_Image->UpdateSource();
-    m_Mask->UpdateSource();
+    {   // the two upstream pipelines (typically two file readers) run side by side
+      const auto* mask = m_Mask;
+      auto other = std::async(std::launch::async, [mask]() { mask->UpdateSource(); });
+      m_Image->UpdateSource();
+      other.get();
+    }
     if (!m_Modified && m_Image->GetBufferPointer() == m_LastImage && m_Mask->GetBufferPointer() == m_LastMask) return;
     const Geometry& g = m_Image->GetGeometry();
     if (m_Mask->GetGeometry().size != g.size)

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -88,7 +89,11 @@ struct ScopedSeconds {
   double& acc;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   explicit ScopedSeconds(double& a) : acc(a) {}
-  ~ScopedSeconds() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  ~ScopedSeconds() {
+    static std::mutex mu;   // files are read concurrently (ReadPair)
+    std::lock_guard<std::mutex> lk(mu);
+    acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
 };
 
 template <typename T>
@@ -162,6 +167,15 @@ typename Image<T>::Pointer Read(const std::string& path) {
     case DT_FLOAT64: convert<T, double>(raw, swapped, slope, inter, out, n); break;
   }
   return img;
+}
+
+// Two files at once (a scan and its mask): inflating a .nii.gz is one serial zlib stream per file, so
+// the second file is read on its own thread.  An error in the first file is the one reported.
+template <typename T1, typename T2>
+std::pair<typename Image<T1>::Pointer, typename Image<T2>::Pointer> ReadPair(const std::string& path1, const std::string& path2) {
+  auto second = std::async(std::launch::async, [&path2]() { return Read<T2>(path2); });
+  typename Image<T1>::Pointer first = Read<T1>(path1);   // throws: `second`'s destructor waits for the thread
+  return std::make_pair(first, second.get());
 }
 
 // One gzip member written by several threads (the way pigz does it): the payload is cut into

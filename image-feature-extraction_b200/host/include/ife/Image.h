@@ -19,6 +19,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <vector>
@@ -59,7 +60,11 @@ public:
         void* p = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = ife_cuda_host_alloc(n * sizeof(T), &p);
-        alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        {
+          static std::mutex mu;   // images are read (and allocated) concurrently
+          std::lock_guard<std::mutex> lk(mu);
+          alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
         if (rc == IFE_OK && p) {
           m_Pinned = true;
         } else {

@@ -71,8 +71,9 @@ int main(int argc, char* argv[]) {
   for (const auto& pr : pairs) {
     std::cout << "Processing " << std::endl << "Image: '" << pr.first << "'" << std::endl << "Mask: '" << pr.second << "'" << std::endl;
     try {
-      auto image = ife::nifti::Read<float>(pr.first);
-      auto mask16 = ife::nifti::Read<unsigned short>(pr.second);
+      auto both = ife::nifti::ReadPair<float, unsigned short>(pr.first, pr.second);   // the two files are inflated concurrently
+      auto image = both.first;
+      auto mask16 = both.second;
       if (mask16->GetSize() != image->GetSize()) throw std::runtime_error("mask and image dimensions differ");
       const size_t n = image->GetNumberOfPixels();
       auto mask = ife::Image<unsigned char>::New();

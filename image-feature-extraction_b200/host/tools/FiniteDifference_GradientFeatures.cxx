@@ -26,8 +26,9 @@ int main(int argc, char* argv[]) {
   const std::string imagePath(cmd.value("image")), maskPath(cmd.value("mask"));
   const std::string baseFileName = ife::Path::join(cmd.value("outdir"), cmd.value("prefix"));
   try {
-    ife::Image<float>::Pointer image = ife::nifti::Read<float>(imagePath);
-    ife::Image<float>::Pointer mask = ife::nifti::Read<float>(maskPath);
+    auto both = ife::nifti::ReadPair<float, float>(imagePath, maskPath);   // the two files are inflated concurrently
+    ife::Image<float>::Pointer image = both.first;
+    ife::Image<float>::Pointer mask = both.second;
     if (mask->GetSize() != image->GetSize()) throw std::runtime_error("mask and image dimensions differ");
     auto out = ife::Image<float>::New();
     out->SetGeometry(image->GetGeometry());

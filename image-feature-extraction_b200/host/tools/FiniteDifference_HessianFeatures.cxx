@@ -42,8 +42,9 @@ int main(int argc, char* argv[]) {
   const std::string baseFileName = ife::Path::join(outDirPath, prefix);
   const std::vector<std::string> featureNames{"eig1", "eig2", "eig3", "LoG", "Curvature", "Frobenius"};
   try {
-    ife::Image<float>::Pointer image = ife::nifti::Read<float>(imagePath);
-    ife::Image<unsigned char>::Pointer mask = ife::nifti::Read<unsigned char>(maskPath);
+    auto both = ife::nifti::ReadPair<float, unsigned char>(imagePath, maskPath);   // the two files are inflated concurrently
+    ife::Image<float>::Pointer image = both.first;
+    ife::Image<unsigned char>::Pointer mask = both.second;
     if (mask->GetSize() != image->GetSize()) throw std::runtime_error("mask and image dimensions differ");
     auto hessianFilter = ife::HessianEigenFeaturesImageFilter<>::New();
     hessianFilter->SetInput(image.get());

@@ -55,8 +55,9 @@ int main(int argc, char* argv[]) {
   }
 
   try {
-    ife::Image<float>::Pointer image = ife::nifti::Read<float>(imagePath);
-    ife::Image<unsigned short>::Pointer mask16 = ife::nifti::Read<unsigned short>(maskPath);
+    auto both = ife::nifti::ReadPair<float, unsigned short>(imagePath, maskPath);   // the two files are inflated concurrently
+    ife::Image<float>::Pointer image = both.first;
+    ife::Image<unsigned short>::Pointer mask16 = both.second;
     const ife::Geometry& g = image->GetGeometry();
     if (mask16->GetSize() != image->GetSize()) throw std::runtime_error("mask and image dimensions differ");
     std::vector<unsigned char> mask(g.voxels());

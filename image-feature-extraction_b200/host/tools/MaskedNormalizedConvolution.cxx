@@ -45,8 +45,9 @@ int main(int argc, char* argv[]) {
   const std::string baseFileName = ife::Path::join(outDirPath, prefix);
   double scale = 0;
   try {
-    ImageType::Pointer image = ife::nifti::Read<float>(imagePath);
-    ImageType::Pointer certainty = ife::nifti::Read<float>(certaintyPath);
+    auto both = ife::nifti::ReadPair<float, float>(imagePath, certaintyPath);   // the two files are inflated concurrently
+    ImageType::Pointer image = both.first;
+    ImageType::Pointer certainty = both.second;
     auto normConvFilter = ife::NormalizedGaussianConvolutionImageFilter<>::New();
     normConvFilter->SetInputImage(image.get());
     normConvFilter->SetInputCertainty(certainty.get());
