@@ -38,6 +38,7 @@ struct Geometry {
 
 // seconds spent allocating (page-locking) pixel storage so far in this process
 inline double& alloc_seconds() { static double s = 0.0; return s; }
+inline std::mutex& alloc_seconds_mutex() { static std::mutex mu; return mu; }   // images are read (and allocated) concurrently
 
 // Contiguous host storage: page-locked when the library can provide it, pageable otherwise
 // (no GPU: the IO classes still work).  Growth leaves new elements uninitialised.
@@ -61,8 +62,7 @@ public:
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = ife_cuda_host_alloc(n * sizeof(T), &p);
         {
-          static std::mutex mu;   // images are read (and allocated) concurrently
-          std::lock_guard<std::mutex> lk(mu);
+          std::lock_guard<std::mutex> lk(alloc_seconds_mutex());
           alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
         if (rc == IFE_OK && p) {
