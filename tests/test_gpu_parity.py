@@ -689,6 +689,33 @@ def test_full_size_invariants_512x512x400(ctx):
         assert np.array_equal(counts[0, k], ref)
 
 
+def test_full_size_plain_gaussian_512x512x400(ctx):
+    """The one-field smoothing at BASELINE's full size through size-independent properties: both kernel
+    families agree bit for bit, a constant stays constant (unit DC gain, edge extension), the result is
+    the true Gaussian to the accuracy of the 4th-order recursive approximation, and an odd plane count
+    (the second warp's stack of planes is one shorter) changes nothing."""
+    import scipy.ndimage
+    shape = (399, 512, 512)
+    rng = np.random.default_rng(5)
+    img = np.ascontiguousarray(rng.standard_normal(shape).astype(np.float32) * 50 - 500)
+    img[200:230, 100:400, 50:300] += 400.0
+    got = ctx.gaussian(img, 2.4)
+    ctx.set_option("tma_passes", 0)
+    try:
+        old = ctx.gaussian(img, 2.4)
+    finally:
+        ctx.set_option("tma_passes", 1)
+    assert bits_equal(got, old)
+    del old
+    assert np.isfinite(got).all()
+    sub = (slice(150, 280), slice(60, 200), slice(20, 120))       # interior block, far from the volume's faces
+    ref = scipy.ndimage.gaussian_filter(img[100:330, 10:250, 0:170].astype(np.float64), 2.4, mode="nearest", truncate=8.0)
+    dev = np.abs(got[sub] - ref[50:180, 50:190, 20:120]).max()
+    assert dev < 0.02 * 400.0, dev                                 # Deriche-type approximation error, not rounding
+    const = np.full((64, 512, 512), 7.25, np.float32)
+    assert np.abs(ctx.gaussian(const, 4.8) - 7.25).max() < 1e-5
+
+
 # ------------------------------------------------------------------------------ z-slabs (one GPU)
 def test_slab_single_rank_equals_whole_volume(ctx):
     shape = (40, 36, 44)
