@@ -240,6 +240,9 @@ int make_map3(ife_cuda_ctx* ctx, CUtensorMap* m, const void* base, bool u8, long
 #ifndef IFE_TMA_MINB_Z
 #define IFE_TMA_MINB_Z 11    // z pass: 20.2 KB of shared memory per block (two roles + the tile of ones)
 #endif
+#ifndef IFE_TMA_MINB_ZF
+#define IFE_TMA_MINB_ZF 9    // z pass with a float certainty: 25.3 KB of shared memory per block
+#endif
 #ifndef IFE_TMA_MINB_X
 #define IFE_TMA_MINB_X 8
 #endif
@@ -272,9 +275,11 @@ int tma_blocks_per_sm(const ife_cuda_ctx* ctx, int axis, long long blocks, int s
 template <int AXIS, int INMODE, bool DIVIDE>
 int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0, const CUtensorMap& i1,
                     const CUtensorMap& o0, const CUtensorMap& o1, const TmaArgs& A, dim3 grid) {
-  constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X : (INMODE == IN_IMG_U8 ? IFE_TMA_MINB_Z : IFE_TMA_MINB_S);
-  constexpr size_t smem_need = (INMODE == IN_IMG_U8 ? kRegionImgU8 + kRegionU8 + kOnesTile
-                                                    : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) + kTmaBarBytes;
+  constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X
+                                    : (INMODE == IN_IMG_U8 ? IFE_TMA_MINB_Z : (INMODE == IN_IMG_F32 ? IFE_TMA_MINB_ZF : IFE_TMA_MINB_S));
+  constexpr size_t smem_need = (INMODE == IN_IMG_U8    ? kRegionImgU8 + kRegionU8 + kOnesTile
+                                : INMODE == IN_IMG_F32 ? kRegionImgF32 + kRegionF32 + kOnesTile
+                                                       : 2 * (AXIS == AX_X ? kRegionX : kRegionF32)) + kTmaBarBytes;
   // Blocks per SM: all blocks of a pass take the same time, so the pass costs ceil(blocks / slots)
   // rounds.  Where one block per SM fewer turns a nearly empty last round into a full one, the
   // shared memory request is padded so that exactly `want` blocks fit (tma_blocks_per_sm()).
@@ -297,8 +302,9 @@ int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0
 // Can the two-field smoothing of an nx x ny x nzb volume take the tensor-map kernels?
 bool tma_passes_usable(const ife_cuda_ctx* ctx, const float* in0, const void* cert, bool cert_is_u8, const float* out0,
                        int nx, int ny, int nzb, const uint8_t* outmask_u8, const float* outmask_f32) {
-  if (!ctx->use_tma || !cert || !cert_is_u8 || outmask_u8 || outmask_f32) return false;
-  if (nx % 16 != 0 || ny >= 65536 || nzb >= 65536) return false;   // 16-byte row pitch of the uint8 mask; grid.y
+  if (!ctx->use_tma || !cert || outmask_u8 || outmask_f32) return false;
+  // row pitch of 16 bytes for every map: nx % 16 for the uint8 certainty, nx % 4 for a float one; grid.y
+  if (nx % (cert_is_u8 ? 16 : 4) != 0 || ny >= 65536 || nzb >= 65536) return false;
   auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   return al(in0) && al(cert) && al(out0) && encode_tiled_fn() != nullptr;
 }
@@ -446,14 +452,16 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
     T.ckpt = (double*)ws.ckpt.ptr;
     {   // z pass: lanes along x, block y = row, samples along z; the multiply c*T is fused into the loads
       IFE_TRY(make_map3(ctx, &mi0, in0, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTRows, false));
-      IFE_TRY(make_map3(ctx, &mi1, cert, true, nx, ny, nzb, nx, plane, 32, 1, kTRows, false));
+      if (cert_is_u8) IFE_TRY(make_map3(ctx, &mi1, cert, true, nx, ny, nzb, nx, plane, 32, 1, kTRows, false));
+      else IFE_TRY(make_map3(ctx, &mi1, cert, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTRows, false));
       IFE_TRY(make_map3(ctx, &mo0, a0, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
       IFE_TRY(make_map3(ctx, &mo1, a1, false, nx, ny, nzb, 4LL * nx, 4 * plane, 32, 1, kTL, false));
       T.in0 = in0; T.in1 = cert;
       T.s_lane = 1; T.s_bx = 32; T.s_by = nx; T.s_n = plane; T.lanes_total = nx;
       T.n = nzb; T.out_lo = kz0; T.out_hi = kz1; T.rows1 = ny;
       ProfScope prof(ctx, K_PASS_Z);
-      IFE_TRY((launch_tma_pass<AX_Z, IN_IMG_U8, false>(ctx, cz, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, ny))));
+      if (cert_is_u8) IFE_TRY((launch_tma_pass<AX_Z, IN_IMG_U8, false>(ctx, cz, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, ny))));
+      else IFE_TRY((launch_tma_pass<AX_Z, IN_IMG_F32, false>(ctx, cz, mi0, mi1, mo0, mo1, T, dim3((nx + 31) / 32, ny))));
     }
     {   // x pass: lanes along y (one line each), block y = plane, samples along x
       IFE_TRY(make_map3(ctx, &mi0, a0 + koff, false, nx, ny, nzk, 4LL * nx, 4 * plane, kXRow, 32, 1, false));

@@ -375,6 +375,10 @@ class Context:
         self._check(self.L.ife_cuda_gaussian(self.h, _ptr(img_ptr), _ptr(out_ptr), _i3(dims), _d3(spacing),
                                              sigma, MEM_DEVICE))
 
+    def normalized_gaussian_dev(self, img_ptr, cert_f32_ptr, out_ptr, dims, sigma, spacing=None, mask_output=False):
+        self._check(self.L.ife_cuda_normalized_gaussian(self.h, _ptr(img_ptr), _ptr(cert_f32_ptr), None, _ptr(out_ptr),
+                                                        _i3(dims), _d3(spacing), sigma, int(mask_output), MEM_DEVICE))
+
     def hessian_eigen_features_dev(self, img_ptr, mask_ptr, out_ptr, dims, sigma, spacing=None,
                                    flags=0):
         self._check(self.L.ife_cuda_hessian_eigen_features(

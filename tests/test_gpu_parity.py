@@ -192,6 +192,41 @@ def test_tensor_map_plain_gaussian_bit_exact(ctx, oracle, arith):
         ctx.set_arith(1)
 
 
+@pytest.mark.parametrize("arith", [1, 0])
+def test_tensor_map_float_certainty_bit_exact(ctx, oracle, arith):
+    """NormalizedGaussianConvolutionImageFilter's own signature, (float T, float c) -> float, through the
+    tensor-map kernels (nx % 4 == 0, no output mask): fractional certainties, zero certainties, ragged tiles."""
+    shapes = [((40, 64, 96), 1.2), ((37, 45, 48), 2.4), ((4, 4, 16), 0.6), ((5, 7, 36), 1.0), ((33, 31, 20), 0.6),
+              ((19, 70, 84), 4.8)]
+    ctx.set_arith(arith)
+    try:
+        for shape, sigma in shapes:      # shape = (nz, ny, nx)
+            img = synth.ct_like(shape, seed=sum(shape) + 2, n_blobs=6)
+            rng = np.random.default_rng(sum(shape))
+            cert = rng.uniform(0, 1, shape).astype(np.float32)
+            cert[rng.uniform(0, 1, shape) < 0.3] = 0.0
+            got = ctx.normalized_gaussian(img, cert, sigma)
+            ctx.set_option("tma_passes", 0)
+            try:
+                old = ctx.normalized_gaussian(img, cert, sigma)
+            finally:
+                ctx.set_option("tma_passes", 1)
+            n, worst = mismatch_report(got, old)
+            assert n == 0, "%s sigma=%g: %d values differ from the cp.async passes (max %g)" % (shape, sigma, n, worst)
+            if np.prod(shape) < 200_000:
+                ref = oracle.normalized_gaussian(img, cert, sigma, arith=arith)
+                assert mismatch_report(got, ref)[0] == 0, "%s sigma=%g vs oracle" % (shape, sigma)
+        # the output mask (the tool's -m flag) keeps the cp.async kernels: same answer as masking afterwards
+        shape = (24, 40, 64)
+        img = synth.ct_like(shape, seed=9, n_blobs=5)
+        cert = (np.random.default_rng(6).uniform(0, 1, shape) < 0.6).astype(np.float32)
+        plain = ctx.normalized_gaussian(img, cert, 1.5)
+        masked = ctx.normalized_gaussian(img, cert, 1.5, mask_output=True)
+        assert bits_equal(masked, np.where(cert != 0, plain, np.float32(0)))
+    finally:
+        ctx.set_arith(1)
+
+
 def test_normalized_gaussian_zero_divisor_rule(ctx, oracle):
     # certainty identically zero -> G(c) == 0 -> itk::DivideImageFilter yields float max
     img = synth.ct_like((8, 8, 8), seed=1, n_blobs=2)
