@@ -272,7 +272,7 @@ int tma_blocks_per_sm(const ife_cuda_ctx* ctx, int axis, long long blocks, int s
   return best == fit ? 0 : best;
 }
 
-template <int AXIS, int INMODE, bool DIVIDE>
+template <int AXIS, int INMODE, bool DIVIDE, int MASKMODE = 0>
 int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0, const CUtensorMap& i1,
                     const CUtensorMap& o0, const CUtensorMap& o1, const TmaArgs& A, dim3 grid) {
   constexpr int MINB = AXIS == AX_X ? IFE_TMA_MINB_X
@@ -286,11 +286,11 @@ int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0
   const int want = tma_blocks_per_sm(ctx, AXIS, (long long)grid.x * grid.y, (int)smem_need);
   const size_t smem = want > 0 ? std::max<size_t>(smem_need, (size_t)(233472 / want - 1024) / 128 * 128) : smem_need;
   if (ctx->arith == IFE_ARITH_FMA) {
-    auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, true, MINB>;
+    auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, true, MINB, MASKMODE>;
     IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 64, smem, ctx->stream()>>>(C, i0, i1, o0, o1, A);
   } else {
-    auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, false, MINB>;
+    auto kern = iir_tma_kernel<AXIS, INMODE, DIVIDE, false, MINB, MASKMODE>;
     IFE_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 64, smem, ctx->stream()>>>(C, i0, i1, o0, o1, A);
   }
@@ -302,7 +302,7 @@ int launch_tma_pass(ife_cuda_ctx* ctx, const GaussCoef& C, const CUtensorMap& i0
 // Can the two-field smoothing of an nx x ny x nzb volume take the tensor-map kernels?
 bool tma_passes_usable(const ife_cuda_ctx* ctx, const float* in0, const void* cert, bool cert_is_u8, const float* out0,
                        int nx, int ny, int nzb, const uint8_t* outmask_u8, const float* outmask_f32) {
-  if (!ctx->use_tma || !cert || outmask_u8 || outmask_f32) return false;
+  if (!ctx->use_tma || !cert) return false;
   // row pitch of 16 bytes for every map: nx % 16 for the uint8 certainty, nx % 4 for a float one; grid.y
   if (nx % (cert_is_u8 ? 16 : 4) != 0 || ny >= 65536 || nzb >= 65536) return false;
   auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
@@ -484,7 +484,16 @@ int smooth_volume(ife_cuda_ctx* ctx, const float* in0, const void* cert, bool ce
       T.s_lane = 1; T.s_bx = 32; T.s_by = plane; T.s_n = nx; T.lanes_total = wx;
       T.n = ny; T.out_lo = ky0; T.out_hi = ky1; T.rows1 = nzk;
       ProfScope prof(ctx, K_PASS_Y);
-      IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, true>(ctx, cy, mi0, mi1, mo0, mo0, T, dim3((wx + 31) / 32, nzk))));
+      const dim3 gy((wx + 31) / 32, nzk);
+      if (outmask_u8) {
+        T.mask = outmask_u8 + yoff;
+        IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, true, 1>(ctx, cy, mi0, mi1, mo0, mo0, T, gy)));
+      } else if (outmask_f32) {
+        T.mask = outmask_f32 + yoff;
+        IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, true, 2>(ctx, cy, mi0, mi1, mo0, mo0, T, gy)));
+      } else {
+        IFE_TRY((launch_tma_pass<AX_Y, IN_FIELDS, true>(ctx, cy, mi0, mi1, mo0, mo0, T, gy)));
+      }
     }
     return IFE_OK;
   }

@@ -120,7 +120,7 @@ int ife_cuda_last_work_dims(const ife_cuda_ctx* ctx, int dims[3]);
  * the cropped path never sees it.  CT volumes are integer-valued; callers with non-finite
  * padding must clear it or switch the option off).
  * "tma_passes" (default 1): normalized convolution with a uint8 certainty on volumes with
- * nx % 16 == 0, or with a float certainty and nx % 4 == 0 (no output mask), and the plain
+ * nx % 16 == 0, or with a float certainty and nx % 4 == 0 (with or without output mask), and the plain
  * Gaussian with nx % 4 == 0 run the tensor-map staged, field-per-warp pass kernels
  * (csrc/iir_tma.cuh); 0 selects the cp.async kernels (same results bit for bit).
  * "march4" (default 1): the fused feature kernel owns four x-adjacent voxels per thread when

@@ -216,13 +216,20 @@ def test_tensor_map_float_certainty_bit_exact(ctx, oracle, arith):
             if np.prod(shape) < 200_000:
                 ref = oracle.normalized_gaussian(img, cert, sigma, arith=arith)
                 assert mismatch_report(got, ref)[0] == 0, "%s sigma=%g vs oracle" % (shape, sigma)
-        # the output mask (the tool's -m flag) keeps the cp.async kernels: same answer as masking afterwards
-        shape = (24, 40, 64)
-        img = synth.ct_like(shape, seed=9, n_blobs=5)
-        cert = (np.random.default_rng(6).uniform(0, 1, shape) < 0.6).astype(np.float32)
-        plain = ctx.normalized_gaussian(img, cert, 1.5)
-        masked = ctx.normalized_gaussian(img, cert, 1.5, mask_output=True)
-        assert bits_equal(masked, np.where(cert != 0, plain, np.float32(0)))
+        # the output mask (the tool's -m flag) is applied where the y pass divides: same answer as masking
+        # afterwards and as the cp.async kernels, float and uint8 certainty, ragged tiles
+        for shape in ((24, 40, 64), (21, 37, 48), (9, 50, 16)):
+            img = synth.ct_like(shape, seed=9, n_blobs=5)
+            for cert in ((np.random.default_rng(6).uniform(0, 1, shape) < 0.6).astype(np.float32),
+                         (np.random.default_rng(7).uniform(0, 1, shape) < 0.5).astype(np.uint8)):
+                plain = ctx.normalized_gaussian(img, cert, 1.5)
+                masked = ctx.normalized_gaussian(img, cert, 1.5, mask_output=True)
+                assert bits_equal(masked, np.where(cert != 0, plain, np.float32(0)))
+                ctx.set_option("tma_passes", 0)
+                try:
+                    assert bits_equal(masked, ctx.normalized_gaussian(img, cert, 1.5, mask_output=True))
+                finally:
+                    ctx.set_option("tma_passes", 1)
     finally:
         ctx.set_arith(1)
 
