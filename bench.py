@@ -259,7 +259,7 @@ def run_reference(args, out_stream):
                    "parallelism": "1 scan per GPU, no data-path collective",
                    "l2": "inputs (525 MB/scan) and every intermediate are larger than the 126 MB L2; no flush needed"},
         "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores,
-                         "kind": "port" if not O.ref_available() else "port+reference-functor",
+                         "kind": "port", "reference_functor_compiled": bool(O.ref_available()),
                          "sample": CPU_SAMPLE + " per step (ITK stages restated; per-voxel functor = reference header)"},
         "e2e": {"value": val, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -317,7 +317,7 @@ def cpu_baseline(ctx, arith):
                      "floor below which bit-exactness buys nothing")
     parity["reference_build_flag_noise"] = noise
     return {"value": img.size * len(SIGMAS) / dt / 1e9, "unit": "Gvoxel/s", "cores": cores,
-            "kind": "port+reference-functor" if O.ref_available() else "port",
+            "kind": "port", "reference_functor_compiled": bool(O.ref_available()),
             "sample": CPU_SAMPLE + ", %.1f s of CPU work (ITK stages restated; per-voxel functor = reference header)" % dt}, parity
 
 
