@@ -41,6 +41,19 @@ public:
         else if (v == "fma") ife_cuda_set_arith(m_Ctx, IFE_ARITH_FMA);
         else throw ExceptionObject(IFE_E_INVALID, "IFE_ARITH must be 'plain' or 'fma'");
       }
+      // IFE_CUDA_OPTIONS="name=value,name=value": ife_cuda_set_option for each (kernel A/B switches)
+      if (const char* o = std::getenv("IFE_CUDA_OPTIONS")) {
+        std::string rest(o);
+        while (!rest.empty()) {
+          const size_t comma = rest.find(',');
+          const std::string kv = rest.substr(0, comma);
+          rest = comma == std::string::npos ? std::string() : rest.substr(comma + 1);
+          const size_t eq = kv.find('=');
+          if (kv.empty()) continue;
+          if (eq == std::string::npos || ife_cuda_set_option(m_Ctx, kv.substr(0, eq).c_str(), std::atoi(kv.c_str() + eq + 1)) != IFE_OK)
+            throw ExceptionObject(IFE_E_INVALID, "IFE_CUDA_OPTIONS: bad entry '" + kv + "'");
+        }
+      }
     }
     return m_Ctx;
   }
