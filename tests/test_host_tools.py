@@ -13,8 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "image-feature-extraction_b200", "bin")
 
 
-def run(tool, *args):
-    return subprocess.run([os.path.join(BIN, tool)] + list(args), capture_output=True, text=True, timeout=600)
+def run(tool, *args, env=None):
+    return subprocess.run([os.path.join(BIN, tool)] + list(args), capture_output=True, text=True, timeout=600,
+                          env=None if env is None else dict(os.environ, **env))
 
 
 def test_host_selftest(tmp_path):
@@ -117,6 +118,25 @@ int main( int argc, char* argv[] ) {
 def test_cli_reports_unreadable_input(tmp_path):
     p = run("ExtractFeatures", "-i", str(tmp_path / "missing.nii.gz"), "-m", "x", "-o", str(tmp_path / "o"), "-s", "1")
     assert p.returncode == 1 and "Failed to process." in p.stderr and "Image:" in p.stderr
+
+
+@pytest.mark.gpu
+def test_tools_honour_ife_cuda_options(tmp_path):
+    """IFE_CUDA_OPTIONS selects kernels (never results) for the command-line tools too; a bad entry is an error."""
+    shape = (20, 24, 32)
+    d = str(tmp_path)
+    nifti_util.write(d + "/img.nii.gz", synth.ct_like(shape, seed=52, n_blobs=6))
+    nifti_util.write(d + "/mask.nii.gz", synth.lung_mask(shape))
+    outs = []
+    for tag, env in (("a", None), ("b", {"IFE_CUDA_OPTIONS": "tma_passes=0,march4=0"})):
+        p = run("ExtractFeatures", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-o", d + "/" + tag, "-s", "1.2", env=env)
+        assert p.returncode == 0, p.stderr
+        outs.append([nifti_util.read("%s/%s_scale_1.200000%s.nii.gz" % (d, tag, nm))[0] for nm in ("GaussianBlur", "Eigenvalue1")])
+    for x, y in zip(*outs):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    p = run("ExtractFeatures", "-i", d + "/img.nii.gz", "-m", d + "/mask.nii.gz", "-o", d + "/c", "-s", "1.2",
+            env={"IFE_CUDA_OPTIONS": "no_such_option=1"})
+    assert p.returncode == 1 and "IFE_CUDA_OPTIONS" in p.stderr
 
 
 def _eig_close(got, ref):
